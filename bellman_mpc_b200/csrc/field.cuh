@@ -1,0 +1,327 @@
+// Multi-limb Montgomery field arithmetic for BLS12-381 Fr (8 x u32) and Fp (12 x u32).
+//
+// Replaces the third-party `bls12_381::Scalar` / `Fp` arithmetic that the reference
+// reaches through ff::Field at src/domain.rs:250-257,294-306 (mul/add/sub_assign in the
+// butterfly) and through group ops at src/multiexp.rs:217,231-232,248.
+//
+// Representation is bit-compatible with bls12_381: little-endian limbs, Montgomery form
+// with R = 2^256 (Fr) / 2^384 (Fp), every value fully reduced to [0, p).  A u32[8] here
+// is the same 32 bytes as the reference's [u64; 4] on a little-endian host.
+//
+// Arithmetic is written as PTX carry chains (mad.lo.cc / madc.hi.cc ...), with the
+// products of even- and odd-indexed limbs accumulated in two separate chains so every
+// chain is a straight run of IMADs.  The same source compiles for the host with the
+// carry flag emulated in a thread-local (used by tests/host_check to validate the
+// algorithms bit-for-bit against the big-integer oracle without a GPU).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BMPC_HD __host__ __device__ __forceinline__
+#define BMPC_D __device__ __forceinline__
+#else
+#define BMPC_HD inline
+#define BMPC_D inline
+#endif
+
+namespace bmpc {
+
+// ----------------------------------------------------------------------------- carry ops
+#if defined(__CUDA_ARCH__)
+BMPC_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BMPC_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BMPC_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BMPC_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BMPC_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BMPC_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// Host emulation of the PTX condition-code register (tests only).
+inline uint32_t& cc_flag() { static thread_local uint32_t f = 0; return f; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cc_flag(); cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cc_flag(); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; cc_flag() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cc_flag(); cc_flag() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cc_flag(); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + cc_flag(); cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + cc_flag(); cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + cc_flag()); }
+#endif
+
+// -------------------------------------------------------------------- field parameters
+// Constants re-derived by oracle/fields.py::self_check(); Fp modulus and INV also appear
+// in the reference itself at src/gt_bytes.rs:20-30.
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;  // -q^-1 mod 2^32
+    BMPC_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return m[i];
+    }
+    BMPC_HD static constexpr uint32_t one(int i) {  // R mod q
+        constexpr uint32_t m[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return m[i];
+    }
+    BMPC_HD static constexpr uint32_t r2(int i) {  // R^2 mod q
+        constexpr uint32_t m[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return m[i];
+    }
+};
+
+struct FpParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    BMPC_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu,
+                                    0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
+                                    0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return m[i];
+    }
+    BMPC_HD static constexpr uint32_t one(int i) {  // R mod p
+        constexpr uint32_t m[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu,
+                                    0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u,
+                                    0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return m[i];
+    }
+    BMPC_HD static constexpr uint32_t r2(int i) {  // R^2 mod p
+        constexpr uint32_t m[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u,
+                                    0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
+                                    0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return m[i];
+    }
+};
+
+// ------------------------------------------------------------------------------ Field
+template <class P>
+struct Field {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    BMPC_HD static Field zero() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    BMPC_HD static Field one() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    BMPC_HD static Field r2() {
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    BMPC_HD bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i];
+        return acc == 0;
+    }
+    BMPC_HD bool operator==(const Field& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= l[i] ^ o.l[i];
+        return acc == 0;
+    }
+    BMPC_HD bool operator!=(const Field& o) const { return !(*this == o); }
+
+    // r = a - p if a >= p else a   (a < 2p)
+    BMPC_HD static void final_sub(uint32_t* r, const uint32_t* a) {
+        uint32_t t[N];
+        t[0] = sub_cc(a[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(a[i], P::mod(i));
+        uint32_t borrow = subc(0, 0);  // 0 or 0xffffffff
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = borrow ? a[i] : t[i];
+    }
+
+    BMPC_HD friend Field operator+(const Field& a, const Field& b) {
+        uint32_t t[N];
+        t[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = addc_cc(a.l[i], b.l[i]);
+        // both moduli leave the top bit(s) of the top limb free: no carry out of limb N-1
+        Field r;
+        final_sub(r.l, t);
+        return r;
+    }
+    BMPC_HD friend Field operator-(const Field& a, const Field& b) {
+        uint32_t t[N];
+        t[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = subc(0, 0);
+        Field r;
+        r.l[0] = add_cc(t[0], borrow & P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(t[i], borrow & P::mod(i));
+        r.l[N - 1] = addc(t[N - 1], borrow & P::mod(N - 1));
+        return r;
+    }
+    BMPC_HD Field neg() const {
+        if (is_zero()) return *this;
+        Field r;
+        r.l[0] = sub_cc(P::mod(0), l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(P::mod(i), l[i]);
+        r.l[N - 1] = subc(P::mod(N - 1), l[N - 1]);
+        return r;
+    }
+    BMPC_HD Field dbl() const { return *this + *this; }
+
+    // One CIOS step: (even, odd) <- ((even, odd) >> 32) + a * bi, then add mi * p so that
+    // limb 0 vanishes.  `even` holds the 2-limb products whose low limb sits at an even
+    // position, `odd` those at an odd position (stored shifted down by one limb).
+    BMPC_HD static void mad_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi,
+                                 bool first) {
+        if (first) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                odd[j] = mul_lo(a[j + 1], bi);
+                odd[j + 1] = mul_hi(a[j + 1], bi);
+                even[j] = mul_lo(a[j], bi);
+                even[j + 1] = mul_hi(a[j], bi);
+            }
+        } else {
+            // `odd` is last step's even array: its limb 0 is zero, its limb 1 lands on
+            // this step's limb 0, limbs 2.. land on odd positions again (shift by two).
+            even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                odd[j] = madc_lo_cc(a[j + 1], bi, odd[j + 2]);
+                odd[j + 1] = madc_hi_cc(a[j + 1], bi, odd[j + 3]);
+            }
+            odd[N - 2] = madc_lo_cc(a[N - 1], bi, 0);
+            odd[N - 1] = madc_hi(a[N - 1], bi, 0);
+            even[0] = mad_lo_cc(a[0], bi, even[0]);
+            even[1] = madc_hi_cc(a[0], bi, even[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                even[j] = madc_lo_cc(a[j], bi, even[j]);
+                even[j + 1] = madc_hi_cc(a[j], bi, even[j + 1]);
+            }
+            odd[N - 1] = addc(odd[N - 1], 0);
+        }
+        uint32_t mi = even[0] * P::INV;
+        odd[0] = mad_lo_cc(P::mod(1), mi, odd[0]);
+        odd[1] = madc_hi_cc(P::mod(1), mi, odd[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            odd[j] = madc_lo_cc(P::mod(j + 1), mi, odd[j]);
+            odd[j + 1] = madc_hi_cc(P::mod(j + 1), mi, odd[j + 1]);
+        }
+        even[0] = mad_lo_cc(P::mod(0), mi, even[0]);
+        even[1] = madc_hi_cc(P::mod(0), mi, even[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            even[j] = madc_lo_cc(P::mod(j), mi, even[j]);
+            even[j + 1] = madc_hi_cc(P::mod(j), mi, even[j + 1]);
+        }
+        odd[N - 1] = addc(odd[N - 1], 0);
+    }
+
+    // Montgomery product a * b * R^-1 mod p, fully reduced.
+    BMPC_HD friend Field operator*(const Field& a, const Field& b) {
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mad_redc(even, odd, a.l, b.l[i], i == 0);
+            mad_redc(odd, even, a.l, b.l[i + 1], false);
+        }
+        // last step left the reduced limb in even[0] (== 0); merge the two chains
+        even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) even[j] = addc_cc(even[j], odd[j + 1]);
+        even[N - 1] = addc(even[N - 1], 0);
+        Field r;
+        final_sub(r.l, even);
+        return r;
+    }
+    BMPC_HD Field sqr() const { return *this * *this; }
+
+    BMPC_HD Field to_mont() const { return *this * r2(); }
+    BMPC_HD Field from_mont() const {
+        Field o = zero();
+        o.l[0] = 1;
+        return *this * o;
+    }
+
+    // this^e for a little-endian multi-word exponent (vartime; setup / one-off use only)
+    BMPC_HD Field pow(const uint32_t* e, int words) const {
+        Field r = one();
+        for (int i = words - 1; i >= 0; i--) {
+            for (int b = 31; b >= 0; b--) {
+                r = r.sqr();
+                if ((e[i] >> b) & 1) r = r * *this;
+            }
+        }
+        return r;
+    }
+    BMPC_HD Field pow_u64(uint64_t e) const {
+        uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+        return pow(w, 2);
+    }
+    // Fermat inverse (0 -> 0).
+    BMPC_HD Field inv() const {
+        uint32_t e[N];
+        e[0] = sub_cc(P::mod(0), 2);
+#pragma unroll
+        for (int i = 1; i < N; i++) e[i] = subc_cc(P::mod(i), 0);
+        return pow(e, N);
+    }
+};
+
+typedef Field<FrParams> Fr;
+typedef Field<FpParams> Fp;
+
+// ------------------------------------------------------------------------------- Fp2
+// Fp2 = Fp[u]/(u^2 + 1)  (bls12_381::Fp2; third-party).
+struct Fp2 {
+    Fp c0, c1;
+    BMPC_HD static Fp2 zero() { return Fp2{Fp::zero(), Fp::zero()}; }
+    BMPC_HD static Fp2 one() { return Fp2{Fp::one(), Fp::zero()}; }
+    BMPC_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    BMPC_HD bool operator==(const Fp2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    BMPC_HD bool operator!=(const Fp2& o) const { return !(*this == o); }
+    BMPC_HD friend Fp2 operator+(const Fp2& a, const Fp2& b) { return Fp2{a.c0 + b.c0, a.c1 + b.c1}; }
+    BMPC_HD friend Fp2 operator-(const Fp2& a, const Fp2& b) { return Fp2{a.c0 - b.c0, a.c1 - b.c1}; }
+    BMPC_HD Fp2 neg() const { return Fp2{c0.neg(), c1.neg()}; }
+    BMPC_HD Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
+    BMPC_HD friend Fp2 operator*(const Fp2& a, const Fp2& b) {
+        Fp t0 = a.c0 * b.c0;
+        Fp t1 = a.c1 * b.c1;
+        Fp t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
+        return Fp2{t0 - t1, t2 - t0 - t1};
+    }
+    BMPC_HD Fp2 sqr() const {
+        Fp s = c0 + c1;
+        Fp d = c0 - c1;
+        Fp m = c0 * c1;
+        return Fp2{s * d, m.dbl()};
+    }
+    BMPC_HD Fp2 inv() const {
+        Fp n = (c0.sqr() + c1.sqr()).inv();
+        return Fp2{c0 * n, (c1 * n).neg()};
+    }
+};
+
+}  // namespace bmpc
