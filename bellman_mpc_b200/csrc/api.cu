@@ -1,0 +1,705 @@
+// libbellman_b200.so -- the C ABI declared in include/bellman_b200.h.
+// This file owns contexts, device memory and the reference's error semantics; kernels and
+// their launch geometry live in ntt.cu / msm_sort.cu / group_g{1,2}.cu / prove.cu.  No field
+// or group arithmetic runs on the host: every constant is computed by a device kernel.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+
+using namespace bmpc;
+
+namespace {
+
+int flags_to_status(uint32_t flags) {
+    // SURVEY 8a'/5: EOF fails every window; an identity only the windows that consume it.
+    if (flags & MSM_FLAG_EOF) return (flags & MSM_FLAG_IDENT_TOP) ? BMPC_ERR_UNEXPECTED_IDENTITY : BMPC_ERR_UNEXPECTED_EOF;
+    if (flags & MSM_FLAG_IDENT_ANY) return BMPC_ERR_UNEXPECTED_IDENTITY;
+    return BMPC_OK;
+}
+
+void write_identity(int group, uint8_t* out) {
+    size_t nb = group == BMPC_G1 ? 96 : 192;
+    memset(out, 0, nb);
+    out[0] = 0x40;
+}
+
+int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                        const uint64_t* d_scalars, size_t n, const uint64_t* d_density,
+                        size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st) {
+    if (!bases || (!out && !d_partial)) return BMPC_ERR_INVALID;
+    if (d_density && density_len != n) return BMPC_ERR_LENGTH_MISMATCH;  // multiexp.rs:273-278
+    if (bases->n >= ((size_t)1 << 31) || base_offset >= ((size_t)1 << 31) || n >= ((size_t)1 << 31))
+        return BMPC_ERR_INVALID;
+    const size_t out_bytes = bases->group == BMPC_G1 ? 96 : 192;
+    if (n == 0) {  // SURVEY 8a'/8: identity, no error
+        if (d_partial) CK(cudaMemsetAsync(d_partial, 0, bmpc_partial_bytes(bases->group), st));
+        if (out) write_identity(bases->group, out);
+        return BMPC_OK;
+    }
+    int rc;
+    uint32_t* d_flags = reinterpret_cast<uint32_t*>(ctx->d_stage);
+    uint8_t* d_bytes = ctx->d_stage + 64;
+    int mode = d_partial ? 1 : 0;
+    MsmPlan p = msm_make_plan(ctx, n, d_density != nullptr);
+    size_t curve_bytes = bases->group == BMPC_G1 ? GroupOps<Fp>::curve_bytes(p) : GroupOps<Fp2>::curve_bytes(p);
+    rc = ws_reserve(ctx, p.sort_bytes + curve_bytes);
+    if (rc) return rc;
+    MsmSorted sorted;
+    rc = msm_sort_run(ctx, p, bases, base_offset, (const uint32_t*)d_scalars, n, (const uint32_t*)d_density,
+                      d_flags, &sorted, st);
+    if (rc) return rc;
+    if (bases->group == BMPC_G1)
+        rc = GroupOps<Fp>::msm_finish(ctx, p, bases, sorted, mode, d_bytes, d_partial, st);
+    else
+        rc = GroupOps<Fp2>::msm_finish(ctx, p, bases, sorted, mode, d_bytes, d_partial, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_stage, ctx->d_stage, 64 + out_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t flags = *reinterpret_cast<uint32_t*>(ctx->h_stage);
+    int status = flags_to_status(flags);
+    if (status == BMPC_OK && out) memcpy(out, ctx->h_stage + 64, out_bytes);
+    return status;
+}
+
+int register_points(bmpc_ctx* ctx, bmpc_bases* b, cudaStream_t st) {
+    size_t nw = (b->n + 31) / 32 + 1;
+    CK(cudaMalloc(&b->d_inf, nw * 4));
+    CK(cudaMemsetAsync(b->d_inf, 0, nw * 4, st));
+    return b->group == BMPC_G1 ? GroupOps<Fp>::inf_bitmap(ctx, b->d_points, b->n, b->d_inf, st)
+                               : GroupOps<Fp2>::inf_bitmap(ctx, b->d_points, b->n, b->d_inf, st);
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int bmpc_ctx_create(int device, bmpc_ctx** out) {
+    if (!out) return BMPC_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return BMPC_ERR_CUDA;
+    bmpc_ctx* ctx = new bmpc_ctx();
+    ctx->device = device;
+    DeviceGuard dg(device);
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_stage, 4096) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stage, 4096) != cudaSuccess) {
+        delete ctx;
+        return BMPC_ERR_CUDA;
+    }
+    const char* ec = getenv("BMPC_MSM_WINDOW");
+    if (ec) ctx->tune_c = atoi(ec);
+    const char* ed = getenv("BMPC_NTT_MAXDEG");
+    if (ed) ctx->tune_maxdeg = atoi(ed);
+    *out = ctx;
+    return BMPC_OK;
+}
+
+void bmpc_ctx_destroy(bmpc_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard dg(ctx->device);
+    cudaDeviceSynchronize();
+    ntt_free_tables(ctx);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* bmpc_last_error(const bmpc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg) {
+    if (!ctx) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->tune_c = msm_window_bits;
+    ctx->tune_maxdeg = ntt_max_deg;
+    return BMPC_OK;
+}
+
+uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------- bases
+int bmpc_bases_register(bmpc_ctx* ctx, int group, const void* points, size_t n, size_t stride,
+                        int form, bmpc_bases** out) {
+    if (!ctx || !out || (group != BMPC_G1 && group != BMPC_G2) || (!points && n)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t pb = group == BMPC_G1 ? 96 : 192;
+    if (stride == 0) stride = pb;
+    if (stride < pb) return BMPC_ERR_INVALID;
+    bmpc_bases* b = new bmpc_bases();
+    b->group = group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    if (n) {
+        if (form == BMPC_FORM_MONT_XY) {
+            CK(cudaMemcpy2DAsync(b->d_points, pb, points, stride, pb, n, cudaMemcpyHostToDevice, st));
+        } else if (form == BMPC_FORM_UNCOMPRESSED_BE) {
+            uint8_t* d_raw;
+            CK(cudaMalloc(&d_raw, n * stride));
+            CK(cudaMemcpyAsync(d_raw, points, n * stride, cudaMemcpyHostToDevice, st));
+            int rcd = group == BMPC_G1 ? GroupOps<Fp>::decode(ctx, d_raw, stride, n, b->d_points, st)
+                                       : GroupOps<Fp2>::decode(ctx, d_raw, stride, n, b->d_points, st);
+            if (rcd) return rcd;
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(d_raw));
+        } else {
+            delete b;
+            return BMPC_ERR_INVALID;
+        }
+    }
+    int rc = register_points(ctx, b, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    *out = b;
+    return BMPC_OK;
+}
+
+int bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont, size_t n,
+                            bmpc_bases** out, void* stream) {
+    if (!ctx || !out || (group != BMPC_G1 && group != BMPC_G2)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    size_t pb = group == BMPC_G1 ? 96 : 192;
+    bmpc_bases* b = new bmpc_bases();
+    b->group = group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    if (n) CK(cudaMemcpyAsync(b->d_points, d_points_mont, n * pb, cudaMemcpyDeviceToDevice, st));
+    int rc = register_points(ctx, b, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    *out = b;
+    return BMPC_OK;
+}
+
+size_t bmpc_bases_len(const bmpc_bases* b) { return b ? b->n : 0; }
+int bmpc_bases_group(const bmpc_bases* b) { return b ? b->group : 0; }
+const void* bmpc_bases_dev_ptr(const bmpc_bases* b) { return b ? b->d_points : nullptr; }
+
+int bmpc_bases_read(bmpc_ctx* ctx, const bmpc_bases* b, size_t start, size_t count, uint8_t* out) {
+    if (!ctx || !b || !out || start + count > b->n) return BMPC_ERR_INVALID;
+    if (!count) return BMPC_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t pb = b->group == BMPC_G1 ? 96 : 192;
+    uint8_t* d_out;
+    CK(cudaMalloc(&d_out, count * pb));
+    int rce = b->group == BMPC_G1
+                  ? GroupOps<Fp>::encode(ctx, (const G1Affine*)b->d_points + start, count, d_out, st)
+                  : GroupOps<Fp2>::encode(ctx, (const G2Affine*)b->d_points + start, count, d_out, st);
+    if (rce) return rce;
+    CK(cudaMemcpyAsync(out, d_out, count * pb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_out));
+    return BMPC_OK;
+}
+
+void bmpc_bases_free(bmpc_ctx* ctx, bmpc_bases* b) {
+    if (!b) return;
+    if (ctx) {
+        DeviceGuard dg(ctx->device);
+        cudaDeviceSynchronize();
+        if (b->d_points) cudaFree(b->d_points);
+        if (b->d_inf) cudaFree(b->d_inf);
+    }
+    delete b;
+}
+
+// ------------------------------------------------------------------------- multiexp
+size_t bmpc_partial_bytes(int group) { return group == BMPC_G1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ); }
+
+int bmpc_multiexp_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                      const uint64_t* d_scalars, size_t n, const uint64_t* d_density_words,
+                      size_t density_len, uint8_t* out, void* stream) {
+    if (!ctx || !out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return multiexp_dev_locked(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len,
+                               out, nullptr, pick_stream(ctx, stream));
+}
+
+int bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                              const uint64_t* d_scalars, size_t n, const uint64_t* d_density_words,
+                              size_t density_len, void* d_partial_out, void* stream) {
+    if (!ctx || !d_partial_out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return multiexp_dev_locked(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len,
+                               nullptr, d_partial_out, pick_stream(ctx, stream));
+}
+
+int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* scalars,
+                  size_t n, const uint64_t* density_words, size_t density_len, uint8_t* out) {
+    if (!ctx || !bases || !out || (!scalars && n)) return BMPC_ERR_INVALID;
+    if (density_words && density_len != n) return BMPC_ERR_LENGTH_MISMATCH;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    uint64_t* d_s = nullptr;
+    uint64_t* d_d = nullptr;
+    size_t dw = (n + 63) / 64;
+    if (n) {
+        CK(cudaMalloc(&d_s, n * 32));
+        CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        if (density_words) {
+            CK(cudaMalloc(&d_d, dw * 8));
+            CK(cudaMemcpyAsync(d_d, density_words, dw * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
+    int rc = multiexp_dev_locked(ctx, bases, base_offset, d_s, n, d_d, density_len, out, nullptr, st);
+    cudaStreamSynchronize(st);
+    if (d_s) cudaFree(d_s);
+    if (d_d) cudaFree(d_d);
+    return rc;
+}
+
+int bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count, uint8_t* out,
+                      void* stream) {
+    if (!ctx || !out || (!d_partials && count)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    size_t ob = group == BMPC_G1 ? 96 : 192;
+    uint8_t* d_bytes = ctx->d_stage + 64;
+    int rcs = group == BMPC_G1 ? GroupOps<Fp>::sum_partials(ctx, d_partials, (uint32_t)count, d_bytes, st)
+                               : GroupOps<Fp2>::sum_partials(ctx, d_partials, (uint32_t)count, d_bytes, st);
+    if (rcs) return rcs;
+    CK(cudaMemcpyAsync(ctx->h_stage, d_bytes, ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out, ctx->h_stage, ob);
+    return BMPC_OK;
+}
+
+// --------------------------------------------------------------------------- domain
+static int domain_alloc(bmpc_ctx* ctx, size_t len, bmpc_domain** out) {
+    // from_coeffs, domain.rs:47-60
+    size_t m = 1;
+    uint32_t exp = 0;
+    while (m < len) {
+        m *= 2;
+        exp += 1;
+        if (exp >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    }
+    bmpc_domain* d = new bmpc_domain();
+    d->m = m;
+    d->exp = exp;
+    CK(cudaMalloc(&d->d, m * sizeof(Fr)));
+    *out = d;
+    return BMPC_OK;
+}
+
+int bmpc_domain_from_coeffs(bmpc_ctx* ctx, const uint64_t* coeffs, size_t len, bmpc_domain** out) {
+    if (!ctx || !out || (!coeffs && len)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    bmpc_domain* d;
+    int rc = domain_alloc(ctx, len, &d);
+    if (rc) return rc;
+    if (len) CK(cudaMemcpyAsync(d->d, coeffs, len * 32, cudaMemcpyHostToDevice, st));
+    if (d->m > len) CK(cudaMemsetAsync(d->d + len, 0, (d->m - len) * 32, st));  // zero == Montgomery zero
+    CK(cudaStreamSynchronize(st));
+    *out = d;
+    return BMPC_OK;
+}
+
+int bmpc_domain_from_coeffs_dev(bmpc_ctx* ctx, const uint64_t* d_coeffs, size_t len, bmpc_domain** out,
+                                void* stream) {
+    if (!ctx || !out || (!d_coeffs && len)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    bmpc_domain* d;
+    int rc = domain_alloc(ctx, len, &d);
+    if (rc) return rc;
+    if (len) CK(cudaMemcpyAsync(d->d, d_coeffs, len * 32, cudaMemcpyDeviceToDevice, st));
+    if (d->m > len) CK(cudaMemsetAsync(d->d + len, 0, (d->m - len) * 32, st));
+    *out = d;
+    return BMPC_OK;
+}
+
+size_t bmpc_domain_len(const bmpc_domain* d) { return d ? d->m : 0; }
+uint32_t bmpc_domain_exp(const bmpc_domain* d) { return d ? d->exp : 0; }
+uint64_t* bmpc_domain_dev_ptr(bmpc_domain* d) { return d ? reinterpret_cast<uint64_t*>(d->d) : nullptr; }
+
+int bmpc_domain_into_coeffs(bmpc_ctx* ctx, const bmpc_domain* d, uint64_t* out) {
+    if (!ctx || !d || !out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    CK(cudaStreamSynchronize(ctx->own_stream));
+    CK(cudaMemcpy(out, d->d, d->m * 32, cudaMemcpyDeviceToHost));
+    return BMPC_OK;
+}
+
+void bmpc_domain_free(bmpc_ctx* ctx, bmpc_domain* d) {
+    if (!d) return;
+    if (ctx) {
+        DeviceGuard dg(ctx->device);
+        cudaDeviceSynchronize();
+        if (d->d) cudaFree(d->d);
+    }
+    delete d;
+}
+
+int bmpc_domain_transform(bmpc_ctx* ctx, bmpc_domain* d, int op, void* stream) {
+    if (!ctx || !d) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return ntt_dev_locked(ctx, d->d, d->exp, op, pick_stream(ctx, stream));
+}
+
+int bmpc_ntt_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_m, int op, void* stream) {
+    if (!ctx || !d_coeffs) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return ntt_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_m, op, pick_stream(ctx, stream));
+}
+
+int bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op) {
+    if (!ctx || !coeffs) return BMPC_ERR_INVALID;
+    if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t m = (size_t)1 << log_m;
+    Fr* d;
+    CK(cudaMalloc(&d, m * sizeof(Fr)));
+    CK(cudaMemcpyAsync(d, coeffs, m * 32, cudaMemcpyHostToDevice, st));
+    int rc = ntt_dev_locked(ctx, d, log_m, op, st);
+    if (rc == BMPC_OK) {
+        cudaError_t e = cudaMemcpyAsync(coeffs, d, m * 32, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BMPC_ERR_CUDA; }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int bmpc_domain_distribute_powers(bmpc_ctx* ctx, bmpc_domain* d, const uint64_t g[4], void* stream) {
+    if (!ctx || !d || !g) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    Fr* d_g = reinterpret_cast<Fr*>(ctx->d_stage + 1024);
+    CK(cudaMemcpyAsync(d_g, g, 32, cudaMemcpyHostToDevice, st));
+    int rcd = fr_distribute_powers(ctx, d->d, d->m, d_g, st);
+    if (rcd) return rcd;
+    CK(cudaStreamSynchronize(st));
+    return BMPC_OK;
+}
+
+int bmpc_domain_z(bmpc_ctx* ctx, const bmpc_domain* d, const uint64_t tau[4], uint64_t out[4]) {
+    if (!ctx || !d || !tau || !out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    Fr* d_t = reinterpret_cast<Fr*>(ctx->d_stage + 1024);
+    CK(cudaMemcpyAsync(d_t, tau, 32, cudaMemcpyHostToDevice, st));
+    int rcz = fr_eval_z(ctx, d_t, d->exp, d_t + 1, st);
+    if (rcz) return rcz;
+    CK(cudaMemcpyAsync(out, d_t + 1, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BMPC_OK;
+}
+
+int bmpc_domain_divide_by_z_on_coset(bmpc_ctx* ctx, bmpc_domain* d, void* stream) {
+    if (!ctx || !d) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    return fr_scale_zinv(ctx, d->d, d->m, d->exp, st);
+}
+
+int bmpc_domain_mul_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* other, void* stream) {
+    if (!ctx || !d || !other) return BMPC_ERR_INVALID;
+    if (d->m != other->m) return BMPC_ERR_LENGTH_MISMATCH;  // assert_eq!, domain.rs:155
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    return fr_pointwise(ctx, 0, d->d, other->d, d->m, st);
+}
+
+int bmpc_domain_sub_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* other, void* stream) {
+    if (!ctx || !d || !other) return BMPC_ERR_INVALID;
+    if (d->m != other->m) return BMPC_ERR_LENGTH_MISMATCH;  // assert_eq!, domain.rs:174
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    return fr_pointwise(ctx, 1, d->d, other->d, d->m, st);
+}
+
+// ---------------------------------------------------------------------- H polynomial
+int bmpc_h_coefficients_dev(bmpc_ctx* ctx, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c, uint32_t log_m,
+                            void* stream) {
+    if (!ctx || !d_a || !d_b || !d_c) return BMPC_ERR_INVALID;
+    if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    size_t m = (size_t)1 << log_m;
+    int rc = ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr)));
+    if (rc) return rc;
+    Fr* t1 = ws_take<Fr>(ctx, m);
+    Fr* t2 = ws_take<Fr>(ctx, m);
+    return h_coefficients_locked(ctx, (Fr*)d_a, (Fr*)d_b, (Fr*)d_c, log_m, t1, t2, st);
+}
+
+int bmpc_h_coefficients(bmpc_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t len,
+                        uint64_t* out, size_t* out_len) {
+    if (!ctx || !a || !b || !c || !out || !out_len) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t m = 1;
+    uint32_t exp = 0;
+    while (m < len) {
+        m *= 2;
+        exp++;
+        if (exp >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    }
+    int rc = ws_reserve(ctx, 5 * ws_need(m, sizeof(Fr)));
+    if (rc) return rc;
+    Fr* d[3];
+    const uint64_t* src[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) {
+        d[k] = ws_take<Fr>(ctx, m);
+        CK(cudaMemcpyAsync(d[k], src[k], len * 32, cudaMemcpyHostToDevice, st));
+        if (m > len) CK(cudaMemsetAsync(d[k] + len, 0, (m - len) * 32, st));
+    }
+    Fr* t1 = ws_take<Fr>(ctx, m);
+    Fr* t2 = ws_take<Fr>(ctx, m);
+    rc = h_coefficients_locked(ctx, d[0], d[1], d[2], exp, t1, t2, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d[0], (m - 1) * 32, cudaMemcpyDeviceToHost, st));  // prover.rs:227-229
+    CK(cudaStreamSynchronize(st));
+    *out_len = m - 1;
+    return BMPC_OK;
+}
+
+int bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* stream) {
+    if (!ctx || (!d_vals && n)) return BMPC_ERR_INVALID;
+    if (!n) return BMPC_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    return fr_pointwise(ctx, 2, (Fr*)d_vals, nullptr, n, st);
+}
+
+// ----------------------------------------------------------------------- create_proof
+int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
+                      const uint64_t s[4], uint8_t proof_out[192]) {
+    if (!ctx || !P || !S || !r || !s || !proof_out) return BMPC_ERR_INVALID;
+    if (!P->h || !P->l || !P->a || !P->b_g1 || !P->b_g2) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    const size_t nc = S->num_constraints, ni = S->num_inputs, na = S->num_aux;
+    size_t m = 1;
+    uint32_t exp = 0;
+    while (m < nc) {
+        m *= 2;
+        exp++;
+        if (exp >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;  // from_coeffs, prover.rs:211
+    }
+    // persistent buffers for this proof (outside the per-MSM scratch arena)
+    Fr *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_in = nullptr, *d_aux = nullptr;
+    uint64_t *d_da = nullptr, *d_dbi = nullptr, *d_dba = nullptr;
+    uint8_t* d_misc = nullptr;  // partials + vk + r,s + proof
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); cudaFree(d_in); cudaFree(d_aux);
+        cudaFree(d_da); cudaFree(d_dbi); cudaFree(d_dba); cudaFree(d_misc);
+    };
+#define CKP(call)                                                            \
+    do {                                                                     \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);   \
+            cleanup();                                                       \
+            return BMPC_ERR_CUDA;                                            \
+        }                                                                    \
+    } while (0)
+#define RCP(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != BMPC_OK) {      \
+            cleanup();             \
+            return rc_;            \
+        }                          \
+    } while (0)
+    CKP(cudaMalloc(&d_a, m * 32)); CKP(cudaMalloc(&d_b, m * 32)); CKP(cudaMalloc(&d_c, m * 32));
+    CKP(cudaMalloc(&d_in, (ni ? ni : 1) * 32)); CKP(cudaMalloc(&d_aux, (na ? na : 1) * 32));
+    size_t dwi = (ni + 63) / 64, dwa = (na + 63) / 64;
+    CKP(cudaMalloc(&d_da, (dwa ? dwa : 1) * 8)); CKP(cudaMalloc(&d_dbi, (dwi ? dwi : 1) * 8));
+    CKP(cudaMalloc(&d_dba, (dwa ? dwa : 1) * 8));
+    CKP(cudaMalloc(&d_misc, 8192));
+    const Fr* srcs[3] = {(const Fr*)S->a, (const Fr*)S->b, (const Fr*)S->c};
+    Fr* dsts[3] = {d_a, d_b, d_c};
+    for (int k = 0; k < 3; k++) {
+        if (nc) CKP(cudaMemcpyAsync(dsts[k], srcs[k], nc * 32, cudaMemcpyHostToDevice, st));
+        if (m > nc) CKP(cudaMemsetAsync(dsts[k] + nc, 0, (m - nc) * 32, st));
+    }
+    if (ni) CKP(cudaMemcpyAsync(d_in, S->input_assignment, ni * 32, cudaMemcpyHostToDevice, st));
+    if (na) CKP(cudaMemcpyAsync(d_aux, S->aux_assignment, na * 32, cudaMemcpyHostToDevice, st));
+    if (dwa) CKP(cudaMemcpyAsync(d_da, S->a_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
+    if (dwi) CKP(cudaMemcpyAsync(d_dbi, S->b_input_density, dwi * 8, cudaMemcpyHostToDevice, st));
+    if (dwa) CKP(cudaMemcpyAsync(d_dba, S->b_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
+
+    // layout of d_misc
+    G1XYZZ* part_g1 = reinterpret_cast<G1XYZZ*>(d_misc);              // 6 x 192
+    G2XYZZ* part_g2 = reinterpret_cast<G2XYZZ*>(d_misc + 1536);       // 2 x 384
+    G1Affine* vk_g1 = reinterpret_cast<G1Affine*>(d_misc + 2560);     // 3 x 96
+    G2Affine* vk_g2 = reinterpret_cast<G2Affine*>(d_misc + 3072);     // 2 x 192
+    Fr* d_rs = reinterpret_cast<Fr*>(d_misc + 3584);                  // 2 x 32
+    uint8_t* d_proof = d_misc + 3840;                                 // 192
+    uint8_t* d_vkraw = d_misc + 4096;                                 // 672
+    uint8_t vkraw[672];
+    memcpy(vkraw, P->alpha_g1, 96); memcpy(vkraw + 96, P->beta_g1, 96); memcpy(vkraw + 192, P->delta_g1, 96);
+    memcpy(vkraw + 288, P->beta_g2, 192); memcpy(vkraw + 480, P->delta_g2, 192);
+    CKP(cudaMemcpyAsync(d_vkraw, vkraw, 672, cudaMemcpyHostToDevice, st));
+    CKP(cudaMemcpyAsync(d_rs, r, 32, cudaMemcpyHostToDevice, st));
+    CKP(cudaMemcpyAsync(d_rs + 1, s, 32, cudaMemcpyHostToDevice, st));
+    RCP(GroupOps<Fp>::decode(ctx, d_vkraw, 96, 3, vk_g1, st));
+    RCP(GroupOps<Fp2>::decode(ctx, d_vkraw + 288, 192, 2, vk_g2, st));
+
+    // H polynomial (prover.rs:210-231)
+    {
+        RCP(ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr))));
+        Fr* t1 = ws_take<Fr>(ctx, m);
+        Fr* t2 = ws_take<Fr>(ctx, m);
+        RCP(h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, st));
+    }
+    // to_le_bits of the assignments (prover.rs:237-250)
+    RCP(fr_pointwise(ctx, 2, d_in, nullptr, ni, st));
+    RCP(fr_pointwise(ctx, 2, d_aux, nullptr, na, st));
+
+    // the eight multiexps (prover.rs:233,252-307); statuses resolved in the reference's await order
+    size_t b_in_total = 0;
+    for (size_t i = 0; i < ni; i++) b_in_total += (S->b_input_density[i / 64] >> (i % 64)) & 1;
+    struct Job { const bmpc_bases* bases; size_t off; const uint64_t* sc; size_t n; const uint64_t* dens; void* out; };
+    Job jobs[8] = {
+        {P->a, 0, (uint64_t*)d_in, ni, nullptr, part_g1 + 0},            // a_inputs   :264-269
+        {P->a, ni, (uint64_t*)d_aux, na, d_da, part_g1 + 1},             // a_aux      :270-275
+        {P->b_g1, 0, (uint64_t*)d_in, ni, d_dbi, part_g1 + 2},           // b_g1_inputs:285-290
+        {P->b_g1, b_in_total, (uint64_t*)d_aux, na, d_dba, part_g1 + 3}, // b_g1_aux   :291-296
+        {P->b_g2, 0, (uint64_t*)d_in, ni, d_dbi, part_g2 + 0},           // b_g2_inputs:301-306
+        {P->b_g2, b_in_total, (uint64_t*)d_aux, na, d_dba, part_g2 + 1}, // b_g2_aux   :307
+        {P->h, 0, (uint64_t*)d_a, m - 1, nullptr, part_g1 + 4},          // h          :233
+        {P->l, 0, (uint64_t*)d_aux, na, nullptr, part_g1 + 5},           // l          :252-257
+    };
+    int statuses[8];
+    for (int j = 0; j < 8; j++) {
+        int rc = multiexp_dev_locked(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens,
+                                     jobs[j].n, nullptr, jobs[j].out, st);
+        if (rc == BMPC_ERR_CUDA || rc == BMPC_ERR_INVALID || rc == BMPC_ERR_LENGTH_MISMATCH) {
+            cleanup();
+            return rc;
+        }
+        statuses[j] = rc;
+    }
+    // subversion check delta != identity comes before the first wait() (prover.rs:309-313)
+    if ((P->delta_g1[0] & 0x40) || (P->delta_g2[0] & 0x40)) {
+        cleanup();
+        return BMPC_ERR_UNEXPECTED_IDENTITY;
+    }
+    for (int j = 0; j < 8; j++)
+        if (statuses[j] != BMPC_OK) {
+            cleanup();
+            return statuses[j];
+        }
+    ProveTailArgs T;
+    T.a_inputs = part_g1 + 0; T.a_aux = part_g1 + 1; T.b1_inputs = part_g1 + 2; T.b1_aux = part_g1 + 3;
+    T.b2_inputs = part_g2 + 0; T.b2_aux = part_g2 + 1; T.h = part_g1 + 4; T.l = part_g1 + 5;
+    T.vk_g1 = vk_g1; T.vk_g2 = vk_g2; T.rs = d_rs; T.proof = d_proof;
+    RCP(prove_tail_launch(ctx, T, st));
+    CKP(cudaMemcpyAsync(ctx->h_stage, d_proof, 192, cudaMemcpyDeviceToHost, st));
+    CKP(cudaStreamSynchronize(st));
+    memcpy(proof_out, ctx->h_stage, 192);
+    cleanup();
+    return BMPC_OK;
+#undef CKP
+#undef RCP
+}
+
+// -------------------------------------------------------------- batch scalar multiply
+int bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* scalars, int per_element,
+                          bmpc_bases** out) {
+    if (!ctx || !in || !scalars || !out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t n = in->n;
+    size_t pb = in->group == BMPC_G1 ? 96 : 192;
+    size_t ns = per_element ? n : 1;
+    uint32_t* d_s;
+    CK(cudaMalloc(&d_s, (ns ? ns : 1) * 32));
+    if (ns) CK(cudaMemcpyAsync(d_s, scalars, ns * 32, cudaMemcpyHostToDevice, st));
+    bmpc_bases* b = new bmpc_bases();
+    b->group = in->group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    int rcb = in->group == BMPC_G1 ? GroupOps<Fp>::batch_mul(ctx, in->d_points, d_s, per_element, n, b->d_points, st)
+                                   : GroupOps<Fp2>::batch_mul(ctx, in->d_points, d_s, per_element, n, b->d_points, st);
+    if (rcb) return rcb;
+    int rc = register_points(ctx, b, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_s));
+    *out = b;
+    return BMPC_OK;
+}
+
+int bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uint64_t* scalars, size_t n,
+                        int scalars_on_device, bmpc_bases** out) {
+    if (!ctx || !base || (!scalars && n) || !out || (group != BMPC_G1 && group != BMPC_G2)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    size_t pb = group == BMPC_G1 ? 96 : 192;
+    size_t xb = group == BMPC_G1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ);
+    uint8_t* d_base_raw;
+    void* d_base;
+    void* d_table;
+    uint32_t* d_s = nullptr;
+    CK(cudaMalloc(&d_base_raw, pb));
+    CK(cudaMalloc(&d_base, pb));
+    CK(cudaMalloc(&d_table, 32 * 256 * xb));
+    CK(cudaMemcpyAsync(d_base_raw, base, pb, cudaMemcpyHostToDevice, st));
+    const uint32_t* sc = (const uint32_t*)scalars;
+    if (!scalars_on_device && n) {
+        CK(cudaMalloc(&d_s, n * 32));
+        CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        sc = d_s;
+    }
+    bmpc_bases* b = new bmpc_bases();
+    b->group = group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    int rcf;
+    if (group == BMPC_G1) {
+        rcf = GroupOps<Fp>::decode(ctx, d_base_raw, pb, 1, d_base, st);
+        if (!rcf) rcf = GroupOps<Fp>::fixed_base_mul(ctx, d_base, d_table, sc, n, b->d_points, st);
+    } else {
+        rcf = GroupOps<Fp2>::decode(ctx, d_base_raw, pb, 1, d_base, st);
+        if (!rcf) rcf = GroupOps<Fp2>::fixed_base_mul(ctx, d_base, d_table, sc, n, b->d_points, st);
+    }
+    if (rcf) return rcf;
+    int rc = register_points(ctx, b, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_base_raw)); CK(cudaFree(d_base)); CK(cudaFree(d_table));
+    if (d_s) CK(cudaFree(d_s));
+    *out = b;
+    return BMPC_OK;
+}
+
+}  // extern "C"

@@ -39,7 +39,7 @@ struct XYZZ {
     BMPC_HD XYZZ neg() const { return XYZZ{X, Y.neg(), ZZ, ZZZ}; }
 
     // 2 * (affine p), p != identity
-    BMPC_HD static XYZZ dbl_affine(const Affine<F>& p) {
+    BMPC_COLD static XYZZ dbl_affine(const Affine<F>& p) {
         F U = p.y.dbl();
         F V = U.sqr();
         F W = U * V;
@@ -51,7 +51,7 @@ struct XYZZ {
         return XYZZ{X3, Y3, V, W};  // y == 0 gives ZZ == 0 == identity, as it must
     }
 
-    BMPC_HD XYZZ dbl() const {
+    BMPC_COLD XYZZ dbl() const {
         if (is_identity()) return *this;
         F U = Y.dbl();
         F V = U.sqr();
@@ -64,7 +64,10 @@ struct XYZZ {
         return XYZZ{X3, Y3, V * ZZ, W * ZZZ};
     }
 
-    // this += affine p (complete)
+    // out-of-line alias for cold callers
+    BMPC_COLD void add_affine_cold(const Affine<F>& p) { add_affine(p); }
+
+    // this += affine p (complete); inlined into the bucket-accumulation loop
     BMPC_HD void add_affine(const Affine<F>& p) {
         if (p.is_identity()) return;
         if (is_identity()) {
@@ -91,7 +94,7 @@ struct XYZZ {
     }
 
     // this += o (complete)
-    BMPC_HD void add(const XYZZ& o) {
+    BMPC_COLD void add(const XYZZ& o) {
         if (o.is_identity()) return;
         if (is_identity()) { *this = o; return; }
         F U1 = X * o.ZZ;
@@ -116,16 +119,16 @@ struct XYZZ {
     }
 
     // canonical affine coordinates (one field inversion)
-    BMPC_HD Affine<F> to_affine() const {
+    BMPC_COLD Affine<F> to_affine() const {
         if (is_identity()) return Affine<F>::identity();
-        F i = (ZZ * ZZZ).inv();          // 1 / (ZZ * ZZZ)
-        F izz = i * ZZZ;                 // 1 / ZZ
-        F izzz = i * ZZ;                 // 1 / ZZZ
-        return Affine<F>{X * izz, Y * izzz};
+        F i = F::mul_cold(ZZ, ZZZ).inv();     // 1 / (ZZ * ZZZ)
+        F izz = F::mul_cold(i, ZZZ);          // 1 / ZZ
+        F izzz = F::mul_cold(i, ZZ);          // 1 / ZZZ
+        return Affine<F>{F::mul_cold(X, izz), F::mul_cold(Y, izzz)};
     }
 
     // this * k for a little-endian multi-word scalar (double-and-add, vartime)
-    BMPC_HD XYZZ mul(const uint32_t* k, int words) const {
+    BMPC_COLD XYZZ mul(const uint32_t* k, int words) const {
         XYZZ r = identity();
         for (int i = words - 1; i >= 0; i--) {
             for (int b = 31; b >= 0; b--) {

@@ -19,9 +19,14 @@
 #if defined(__CUDACC__)
 #define BMPC_HD __host__ __device__ __forceinline__
 #define BMPC_D __device__ __forceinline__
+// cold-path functions (inversion, exponentiation, full point addition ...) are kept out of
+// line: inlining every 600-instruction Montgomery product into them makes device
+// compilation explode and buys nothing where they run.
+#define BMPC_COLD __host__ __device__ __noinline__
 #else
 #define BMPC_HD inline
 #define BMPC_D inline
+#define BMPC_COLD inline
 #endif
 
 namespace bmpc {
@@ -257,6 +262,8 @@ struct Field {
         return r;
     }
     BMPC_HD Field sqr() const { return *this * *this; }
+    // out-of-line product for cold paths
+    BMPC_COLD static Field mul_cold(const Field& a, const Field& b) { return a * b; }
 
     BMPC_HD Field to_mont() const { return *this * r2(); }
     BMPC_HD Field from_mont() const {
@@ -266,12 +273,16 @@ struct Field {
     }
 
     // this^e for a little-endian multi-word exponent (vartime; setup / one-off use only)
-    BMPC_HD Field pow(const uint32_t* e, int words) const {
+    BMPC_COLD Field pow(const uint32_t* e, int words) const {
         Field r = one();
+        bool started = false;
         for (int i = words - 1; i >= 0; i--) {
             for (int b = 31; b >= 0; b--) {
-                r = r.sqr();
-                if ((e[i] >> b) & 1) r = r * *this;
+                if (started) r = mul_cold(r, r);
+                if ((e[i] >> b) & 1) {
+                    r = mul_cold(r, *this);
+                    started = true;
+                }
             }
         }
         return r;
@@ -281,7 +292,7 @@ struct Field {
         return pow(w, 2);
     }
     // Fermat inverse (0 -> 0).
-    BMPC_HD Field inv() const {
+    BMPC_COLD Field inv() const {
         uint32_t e[N];
         e[0] = sub_cc(P::mod(0), 2);
 #pragma unroll
@@ -318,10 +329,11 @@ struct Fp2 {
         Fp m = c0 * c1;
         return Fp2{s * d, m.dbl()};
     }
-    BMPC_HD Fp2 inv() const {
-        Fp n = (c0.sqr() + c1.sqr()).inv();
-        return Fp2{c0 * n, (c1 * n).neg()};
+    BMPC_COLD Fp2 inv() const {
+        Fp n = (Fp::mul_cold(c0, c0) + Fp::mul_cold(c1, c1)).inv();
+        return Fp2{Fp::mul_cold(c0, n), Fp::mul_cold(c1, n).neg()};
     }
+    BMPC_COLD static Fp2 mul_cold(const Fp2& a, const Fp2& b) { return a * b; }
 };
 
 }  // namespace bmpc

@@ -1,0 +1,100 @@
+// Host-side launchers for the curve-typed kernels, instantiated once per group
+// (group_g1.cu: F = Fp, group_g2.cu: F = Fp2).
+#pragma once
+#include "group_kernels.cuh"
+#include "internal.h"
+
+namespace bmpc {
+
+template <class F>
+size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
+    return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.g.W * p.nblk, sizeof(XYZZ<F>)) + 1024;
+}
+
+template <class F>
+int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, const MsmSorted& s,
+                            int mode, uint8_t* d_out_bytes, void* d_out_xyzz, cudaStream_t st) {
+    const MsmGeom& g = p.g;
+    XYZZ<F>* partials = ws_take<XYZZ<F>>(ctx, p.max_tasks);
+    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)g.W * p.nblk);
+    if (!partials || !blk_out) {
+        ctx->err = "msm workspace carve failed (curve)";
+        return BMPC_ERR_INVALID;
+    }
+    const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
+    uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
+    LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.off, s.toff, p.nb, g.L, partials);
+    {
+        size_t smem = 128 * sizeof(XYZZ<F>);
+        CK(cudaFuncSetAttribute(msm_combine_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(ctx, msm_combine_heavy_kernel<F>, 148 * 2, 128, smem, st, s.toff, s.heavy, s.heavy_count, partials);
+    }
+    {
+        size_t smem = (size_t)p.rblock * sizeof(XYZZ<F>);
+        CK(cudaFuncSetAttribute(msm_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(128 * sizeof(XYZZ<F>))));
+        dim3 grid(p.nblk, g.W);
+        LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, partials, s.toff, g.B, p.S, blk_out);
+    }
+    {
+        size_t smem = (size_t)g.W * sizeof(XYZZ<F>);
+        CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(ctx, msm_final_kernel<F>, 1, 32, smem, st, blk_out, g.W, p.nblk, g.c, mode, d_out_bytes,
+               reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+    }
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::sum_partials(bmpc_ctx* ctx, const void* d_parts, uint32_t count, uint8_t* d_out_bytes,
+                              cudaStream_t st) {
+    LAUNCH(ctx, msm_sum_partials_kernel<F>, 1, 1, 0, st, reinterpret_cast<const XYZZ<F>*>(d_parts), count, d_out_bytes);
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size_t n, void* d_points,
+                        cudaStream_t st) {
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, decode_uncompressed_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st, d_raw, stride, n,
+           reinterpret_cast<Affine<F>*>(d_points));
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::encode(bmpc_ctx* ctx, const void* d_points, size_t n, uint8_t* d_out, cudaStream_t st) {
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, encode_uncompressed_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,
+           reinterpret_cast<const Affine<F>*>(d_points), n, d_out);
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::inf_bitmap(bmpc_ctx* ctx, const void* d_points, size_t n, uint32_t* d_bitmap, cudaStream_t st) {
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, inf_bitmap_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,
+           reinterpret_cast<const Affine<F>*>(d_points), n, d_bitmap);
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::batch_mul(bmpc_ctx* ctx, const void* d_in, const uint32_t* d_scalars, int per_element,
+                           size_t n, void* d_out, cudaStream_t st) {
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, batch_scalar_mul_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,
+           reinterpret_cast<const Affine<F>*>(d_in), d_scalars, per_element, n, reinterpret_cast<Affine<F>*>(d_out));
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table, const uint32_t* d_scalars,
+                                size_t n, void* d_out, cudaStream_t st) {
+    LAUNCH(ctx, fixed_base_table_kernel<F>, 1, 32, 0, st, reinterpret_cast<const Affine<F>*>(d_base),
+           reinterpret_cast<XYZZ<F>*>(d_table));
+    if (n)
+        LAUNCH(ctx, fixed_base_mul_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,
+               reinterpret_cast<const XYZZ<F>*>(d_table), d_scalars, n, reinterpret_cast<Affine<F>*>(d_out));
+    return BMPC_OK;
+}
+
+}  // namespace bmpc

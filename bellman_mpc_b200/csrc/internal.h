@@ -1,0 +1,208 @@
+// Internal host-side declarations shared by the translation units of libbellman_b200.so.
+// (api.cu = C ABI, ntt.cu = EvaluationDomain kernels, msm_sort.cu = digit/sort kernels,
+//  group_g1.cu / group_g2.cu = curve kernels instantiated per group, prove.cu = proof tail.)
+#pragma once
+#include "../../include/bellman_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "curve.cuh"
+
+namespace bmpc {
+
+constexpr uint32_t SMALL_LOG = 10;  // largest in-block NTT radix 2^10
+
+enum TableKind {
+    K_TW_FWD = 0, K_TW_INV, K_G, K_G_MINV, K_GINV_MINV, K_GINV_MINV_ZINV_CANON, K_COUNT
+};
+
+struct DevTable {
+    Fr* hi = nullptr;
+    Fr* lo = nullptr;
+    uint32_t lo_bits = 0, hi_n = 0;
+    bool ready = false;
+};
+
+struct DomainTables {
+    Fr* d_consts = nullptr;  // 10 x Fr, see domain_consts_kernel
+    Fr h_consts[10];
+    DevTable t[K_COUNT];
+};
+
+}  // namespace bmpc
+
+struct bmpc_ctx {
+    int device = 0;
+    std::string err;
+    std::mutex mu;
+    uint64_t launches = 0;
+    int tune_c = 0, tune_maxdeg = 0;
+    cudaStream_t own_stream = nullptr;
+    // scratch arena (grown on demand, reused across calls)
+    char* ws = nullptr;
+    size_t ws_size = 0, ws_used = 0;
+    // staging for small results
+    uint8_t* h_stage = nullptr;  // 4 KB pinned
+    uint8_t* d_stage = nullptr;  // 4 KB
+    std::map<uint32_t, bmpc::DomainTables> domains;
+    bmpc::Fr* tw_small[2] = {nullptr, nullptr};  // fwd / inv powers of the 2^SMALL_LOG-th root
+};
+
+struct bmpc_bases {
+    int group = 0;
+    size_t n = 0;
+    void* d_points = nullptr;   // Affine<Fp>[n] or Affine<Fp2>[n], Montgomery
+    uint32_t* d_inf = nullptr;  // identity bitmap
+};
+
+struct bmpc_domain {
+    bmpc::Fr* d = nullptr;
+    size_t m = 0;
+    uint32_t exp = 0;
+};
+
+namespace bmpc {
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+            return BMPC_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+#define LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                           \
+    do {                                                                              \
+        kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                           \
+        (ctx)->launches++;                                                            \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess) {                                                      \
+            (ctx)->err = std::string(#kernel) + ": " + cudaGetErrorString(e_);        \
+            return BMPC_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline size_t ws_need(size_t count, size_t elem) { return align_up(count * elem, 256); }
+
+// Arena: reserve once per call with the total, then carve.
+inline int ws_reserve(bmpc_ctx* ctx, size_t bytes) {
+    ctx->ws_used = 0;
+    if (bytes <= ctx->ws_size) return BMPC_OK;
+    CK(cudaDeviceSynchronize());
+    if (ctx->ws) CK(cudaFree(ctx->ws));
+    ctx->ws = nullptr;
+    ctx->ws_size = 0;
+    size_t want = align_up(bytes + (bytes >> 3), 1 << 20);
+    CK(cudaMalloc(&ctx->ws, want));
+    ctx->ws_size = want;
+    return BMPC_OK;
+}
+template <class T>
+inline T* ws_take(bmpc_ctx* ctx, size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (ctx->ws_used + bytes > ctx->ws_size) return nullptr;
+    T* p = reinterpret_cast<T*>(ctx->ws + ctx->ws_used);
+    ctx->ws_used += bytes;
+    return p;
+}
+inline cudaStream_t pick_stream(bmpc_ctx* ctx, void* stream) {
+    return stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->own_stream;
+}
+
+// ---------------------------------------------------------------- ntt.cu
+int ntt_dev_locked(bmpc_ctx* ctx, Fr* d, uint32_t logm, int op, cudaStream_t st);
+int h_coefficients_locked(bmpc_ctx* ctx, Fr* a, Fr* b, Fr* c, uint32_t logm, Fr* t1, Fr* t2,
+                          cudaStream_t st);
+int fr_pointwise(bmpc_ctx* ctx, int what, Fr* a, const Fr* b, size_t n, cudaStream_t st);  // 0 mul 1 sub 2 to_canonical
+int fr_scale_zinv(bmpc_ctx* ctx, Fr* a, size_t m, uint32_t logm, cudaStream_t st);
+int fr_distribute_powers(bmpc_ctx* ctx, Fr* a, size_t m, const Fr* d_g, cudaStream_t st);
+int fr_eval_z(bmpc_ctx* ctx, const Fr* d_tau, uint32_t logm, Fr* d_out, cudaStream_t st);
+void ntt_free_tables(bmpc_ctx* ctx);
+
+// ------------------------------------------------------------- msm_sort.cu
+enum { MSM_FLAG_EOF = 1, MSM_FLAG_IDENT_ANY = 2, MSM_FLAG_IDENT_TOP = 4 };
+
+struct MsmGeom {
+    uint32_t c;        // window bits
+    uint32_t W;        // number of windows = 255 / c + 1
+    uint32_t B;        // buckets per window = 2^(c-1)  (signed digits)
+    uint32_t L;        // max points per accumulate task
+    uint32_t c_ref;    // the reference's window size for this n (error precedence only)
+    uint32_t top_skip; // bit offset of the reference's highest window
+};
+
+struct MsmPlan {
+    MsmGeom g;
+    uint32_t nb;  // total buckets
+    size_t max_pairs, max_tasks;
+    uint32_t tpw, rblock, S, nblk;
+    size_t sort_bytes;  // scratch for everything except the curve-typed buffers
+};
+
+struct MsmSorted {      // outputs of the sort stage (device pointers into the arena)
+    uint32_t* sorted;   // base index | sign << 31, grouped by bucket
+    uint32_t* off;      // nb + 1 bucket offsets
+    uint32_t* toff;     // nb + 1 task offsets
+    uint32_t* heavy;    // nb + 1 scratch for the heavy-bucket list
+    uint32_t* heavy_count;
+};
+
+MsmPlan msm_make_plan(bmpc_ctx* ctx, size_t n, bool has_density);
+// count -> scan -> scatter; raises EOF / identity flags into d_flags[0]
+int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,
+                 const uint32_t* d_scalars, size_t n, const uint32_t* d_density, uint32_t* d_flags,
+                 MsmSorted* out, cudaStream_t st);
+
+// -------------------------------------------------- group_g1.cu / group_g2.cu
+template <class F>
+struct GroupOps {
+    static size_t curve_bytes(const MsmPlan& p);
+    // accumulate -> combine -> reduce -> final.  mode 0: uncompressed bytes to d_out_bytes;
+    // mode 1: XYZZ partial to d_out_xyzz.
+    static int msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, const MsmSorted& s,
+                          int mode, uint8_t* d_out_bytes, void* d_out_xyzz, cudaStream_t st);
+    static int sum_partials(bmpc_ctx* ctx, const void* d_parts, uint32_t count, uint8_t* d_out_bytes,
+                            cudaStream_t st);
+    static int decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size_t n, void* d_points,
+                      cudaStream_t st);
+    static int encode(bmpc_ctx* ctx, const void* d_points, size_t n, uint8_t* d_out, cudaStream_t st);
+    static int inf_bitmap(bmpc_ctx* ctx, const void* d_points, size_t n, uint32_t* d_bitmap, cudaStream_t st);
+    static int batch_mul(bmpc_ctx* ctx, const void* d_in, const uint32_t* d_scalars, int per_element,
+                         size_t n, void* d_out, cudaStream_t st);
+    static int fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table, const uint32_t* d_scalars,
+                              size_t n, void* d_out, cudaStream_t st);
+};
+
+// ---------------------------------------------------------------- prove.cu
+struct ProveTailArgs {
+    // multiexp partial sums (XYZZ), in the order the reference awaits them (prover.rs:328-343)
+    const G1XYZZ* a_inputs; const G1XYZZ* a_aux;
+    const G1XYZZ* b1_inputs; const G1XYZZ* b1_aux;
+    const G2XYZZ* b2_inputs; const G2XYZZ* b2_aux;
+    const G1XYZZ* h; const G1XYZZ* l;
+    // vk: alpha_g1, beta_g1, delta_g1 (G1Affine[3]); beta_g2, delta_g2 (G2Affine[2])
+    const G1Affine* vk_g1; const G2Affine* vk_g2;
+    const Fr* rs;   // r, s in Montgomery form
+    uint8_t* proof; // 192 B
+};
+int prove_tail_launch(bmpc_ctx* ctx, const ProveTailArgs& args, cudaStream_t st);
+
+}  // namespace bmpc

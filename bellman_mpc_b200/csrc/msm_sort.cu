@@ -1,0 +1,126 @@
+// MSM stages 1-3 (host side): geometry, density prefix popcount, digit histogram, scans,
+// counting-sort scatter.  Reference: src/multiexp.rs:191-223 (the per-window scan that this
+// replaces) and :254-281 (window rule, density length).
+#include <cmath>
+
+#include "msm_sort_kernels.cuh"
+
+namespace bmpc {
+
+static uint32_t reference_window(size_t n) {  // multiexp.rs:267-271
+    if (n < 32) return 3;
+    return (uint32_t)std::ceil(std::log((double)(uint32_t)n));
+}
+
+static inline size_t scan_chunks_words(uint32_t n) {
+    return (n + BMPC_SCAN_CHUNK - 1) / BMPC_SCAN_CHUNK + 2;
+}
+
+MsmPlan msm_make_plan(bmpc_ctx* ctx, size_t n, bool has_density) {
+    MsmPlan p;
+    MsmGeom& g = p.g;
+    uint32_t c;
+    if (ctx->tune_c) c = (uint32_t)ctx->tune_c;
+    else {
+        uint32_t lg = 0;
+        while (((size_t)1 << (lg + 1)) <= n) lg++;
+        c = lg > 8 ? lg - 4 : 4;
+        if (c > 16) c = 16;
+    }
+    if (c < 2) c = 2;
+    if (c > 20) c = 20;
+    g.c = c;
+    g.W = 255 / c + 1;
+    g.B = 1u << (c - 1);
+    size_t avg = n / g.B;
+    g.L = (uint32_t)(2 * avg < 64 ? 64 : 2 * avg);
+    g.c_ref = reference_window(n);
+    g.top_skip = (254 / g.c_ref) * g.c_ref;
+    p.nb = g.W * g.B;
+    p.max_pairs = n * g.W;
+    p.max_tasks = p.max_pairs / g.L + p.nb + 1;
+    p.tpw = g.B < 1024 ? g.B : 1024;
+    p.rblock = p.tpw < 128 ? p.tpw : 128;
+    p.S = g.B / p.tpw;
+    p.nblk = p.tpw / p.rblock;
+    size_t b = 0;
+    size_t nw32 = (n + 31) / 32;
+    if (has_density) b += ws_need(nw32 + 1, 4) * 2 + ws_need(scan_chunks_words((uint32_t)nw32), 4);
+    b += ws_need(p.nb + 1, 4) * 5;  // hist, off, toff, cursor, heavy
+    b += ws_need(scan_chunks_words(p.nb), 4);
+    b += ws_need(p.max_pairs + 1, 4);  // sorted
+    b += ws_need(64, 4);
+    p.sort_bytes = b + 4096;
+    return p;
+}
+
+// out[n+1] = exclusive scan of xform(in); `chunks` scratch of scan_chunks_words(n) words
+static int run_scan(bmpc_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t L, uint32_t* chunks,
+                    uint32_t* out, cudaStream_t st) {
+    uint32_t nchunks = (n + BMPC_SCAN_CHUNK - 1) / BMPC_SCAN_CHUNK;
+    if (nchunks == 0) nchunks = 1;
+    LAUNCH(ctx, scan_phase1_kernel, nchunks, BMPC_SCAN_THREADS, 0, st, in, n, L, chunks);
+    LAUNCH(ctx, scan_phase2_kernel, 1, BMPC_SCAN_THREADS, 0, st, chunks, nchunks);
+    LAUNCH(ctx, scan_phase3_kernel, nchunks, BMPC_SCAN_THREADS, 0, st, in, n, L, chunks, nchunks, out);
+    return BMPC_OK;
+}
+
+int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,
+                 const uint32_t* d_scalars, size_t n, const uint32_t* d_density, uint32_t* d_flags,
+                 MsmSorted* out, cudaStream_t st) {
+    const MsmGeom& g = p.g;
+    MsmInput in;
+    in.scalars = d_scalars;
+    in.n = n;
+    in.density = d_density;
+    in.word_prefix = nullptr;
+    in.base_offset = (uint32_t)base_offset;
+    in.bases_len = (uint32_t)bases->n;
+    in.inf_bitmap = bases->d_inf;
+    CK(cudaMemsetAsync(d_flags, 0, 16, st));
+    if (d_density) {
+        uint32_t nw32 = (uint32_t)((n + 31) / 32);
+        uint32_t* pc = ws_take<uint32_t>(ctx, nw32 + 1);
+        uint32_t* prefix = ws_take<uint32_t>(ctx, nw32 + 1);
+        uint32_t* chunks = ws_take<uint32_t>(ctx, scan_chunks_words(nw32));
+        if (!pc || !prefix || !chunks) {
+            ctx->err = "msm workspace carve failed (density)";
+            return BMPC_ERR_INVALID;
+        }
+        LAUNCH(ctx, popc_words_kernel, (nw32 + 255) / 256, 256, 0, st, d_density, nw32, (uint32_t)n, pc);
+        int rc = run_scan(ctx, pc, nw32, 0, chunks, prefix, st);
+        if (rc) return rc;
+        in.word_prefix = prefix;
+    }
+    uint32_t* hist = ws_take<uint32_t>(ctx, p.nb + 1);
+    uint32_t* off = ws_take<uint32_t>(ctx, p.nb + 1);
+    uint32_t* toff = ws_take<uint32_t>(ctx, p.nb + 1);
+    uint32_t* cursor = ws_take<uint32_t>(ctx, p.nb + 1);
+    uint32_t* heavy = ws_take<uint32_t>(ctx, p.nb + 1);
+    uint32_t* chunks = ws_take<uint32_t>(ctx, scan_chunks_words(p.nb));
+    uint32_t* sorted = ws_take<uint32_t>(ctx, p.max_pairs + 1);
+    uint32_t* heavy_count = ws_take<uint32_t>(ctx, 64);
+    if (!hist || !off || !toff || !cursor || !heavy || !chunks || !sorted || !heavy_count) {
+        ctx->err = "msm workspace carve failed";
+        return BMPC_ERR_INVALID;
+    }
+    CK(cudaMemsetAsync(hist, 0, (size_t)(p.nb + 1) * 4, st));
+    CK(cudaMemsetAsync(heavy_count, 0, 4, st));
+    uint32_t nblocks = (uint32_t)((n + 255) / 256);
+    LAUNCH(ctx, msm_count_kernel, nblocks, 256, 0, st, in, g, hist, d_flags);
+    int rc = run_scan(ctx, hist, p.nb, 0, chunks, off, st);
+    if (rc) return rc;
+    rc = run_scan(ctx, hist, p.nb, g.L, chunks, toff, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cursor, off, (size_t)p.nb * 4, cudaMemcpyDeviceToDevice, st));
+    LAUNCH(ctx, msm_scatter_kernel, nblocks, 256, 0, st, in, g, cursor, sorted);
+    LAUNCH(ctx, msm_find_heavy_kernel, (p.nb + 255) / 256, 256, 0, st, toff, p.nb, heavy, heavy_count);
+    out->sorted = sorted;
+    out->off = off;
+    out->toff = toff;
+    out->heavy = heavy;
+    out->heavy_count = heavy_count;
+    return BMPC_OK;
+}
+
+}  // namespace bmpc

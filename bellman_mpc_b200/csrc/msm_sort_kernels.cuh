@@ -1,0 +1,203 @@
+// Digit extraction, density -> base index resolution and counting sort for the MSM
+// (stages 1-3 of the pipeline described in group_kernels.cuh).
+#pragma once
+#include "internal.h"
+
+namespace bmpc {
+
+struct MsmInput {
+    const uint32_t* scalars;       // n x 8 u32 canonical little-endian
+    size_t n;
+    const uint32_t* density;       // NULL = FullDensity; else 32-bit view of the u64 words
+    const uint32_t* word_prefix;   // exclusive popcount prefix per 32-bit density word
+    uint32_t base_offset;
+    uint32_t bases_len;
+    const uint32_t* inf_bitmap;    // bit per base: 1 = identity
+};
+
+__device__ __forceinline__ void load_scalar(const uint32_t* p, uint32_t s[8]) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+}
+
+// bits [pos, pos + c) of a 256-bit little-endian integer (bits >= 256 read as zero), c <= 24
+__device__ __forceinline__ uint32_t get_bits(const uint32_t s[8], uint32_t pos, uint32_t c) {
+    uint32_t w = pos >> 5, sh = pos & 31;
+    uint32_t lo = w < 8 ? s[w] : 0u;
+    uint32_t hi = (w + 1) < 8 ? s[w + 1] : 0u;
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// Resolves position i -> (dense?, base index); returns false if nothing is consumed.
+__device__ __forceinline__ bool resolve_base(const MsmInput& in, size_t i, uint32_t& base_idx) {
+    if (in.density) {
+        uint32_t wi = (uint32_t)(i >> 5), bit = (uint32_t)(i & 31);
+        uint32_t word = __ldg(in.density + wi);
+        if (!((word >> bit) & 1u)) return false;
+        uint32_t rank = __ldg(in.word_prefix + wi) + __popc(word & ((1u << bit) - 1u));
+        base_idx = in.base_offset + rank;
+    } else {
+        base_idx = in.base_offset + (uint32_t)i;
+    }
+    return true;
+}
+
+// Shared by count and scatter: calls f(window, bucket_in_window, negative) for every non-zero
+// signed digit.  Returns false when the position contributes nothing.
+template <class Fn>
+__device__ __forceinline__ bool for_each_digit(const MsmInput& in, const MsmGeom& g, size_t i,
+                                               uint32_t* flags, bool raise, uint32_t& base_idx,
+                                               Fn f) {
+    if (!resolve_base(in, i, base_idx)) return false;
+    if (base_idx >= in.bases_len) {  // Source::{next,skip} -> UnexpectedEof (multiexp.rs:55-61,74-80)
+        if (raise) atomicOr(flags, (uint32_t)MSM_FLAG_EOF);
+        return false;
+    }
+    uint32_t s[8];
+    load_scalar(in.scalars + i * 8, s);
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return false;  // skip(1)
+    if ((__ldg(in.inf_bitmap + (base_idx >> 5)) >> (base_idx & 31)) & 1u) {
+        // next() on an identity base -> UnexpectedIdentity (multiexp.rs:63-65); which error wins
+        // depends on whether the reference's top window would have consumed it.
+        if (raise) {
+            uint32_t fl = MSM_FLAG_IDENT_ANY;
+            if (get_bits(s, g.top_skip, g.c_ref) != 0) fl |= MSM_FLAG_IDENT_TOP;
+            atomicOr(flags, fl);
+        }
+        return false;
+    }
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (g.c - 1);
+    for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t d = get_bits(s, w * g.c, g.c) + carry;
+        bool neg = d > half;
+        if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
+        if (d != 0) f(w, d - 1u, neg);
+    }
+    return true;
+}
+
+__global__ void msm_count_kernel(MsmInput in, MsmGeom g, uint32_t* hist, uint32_t* flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    uint32_t base_idx;
+    for_each_digit(in, g, i, flags, true, base_idx,
+                   [&](uint32_t w, uint32_t b, bool) { atomicAdd(hist + (size_t)w * g.B + b, 1u); });
+}
+
+__global__ void msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uint32_t* sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.n) return;
+    uint32_t base_idx;
+    for_each_digit(in, g, i, nullptr, false, base_idx, [&](uint32_t w, uint32_t b, bool neg) {
+        uint32_t pos = atomicAdd(cursor + (size_t)w * g.B + b, 1u);
+        sorted[pos] = base_idx | (neg ? 0x80000000u : 0u);
+    });
+}
+
+// ---------------------------------------------------------------- density prefix popcount
+__global__ void popc_words_kernel(const uint32_t* words, uint32_t nwords, uint32_t nbits,
+                                  uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t w = words[i];
+    uint32_t rem = nbits - i * 32u;           // bits of this word that are inside the map
+    if (rem < 32u) w &= (1u << rem) - 1u;
+    out[i] = __popc(w);
+}
+
+// ------------------------------------------------------------------ exclusive scan (u32)
+// Three phases over chunks of SCAN_CHUNK elements; `mode` 1 scans ceil(x / L) instead of x.
+#define BMPC_SCAN_THREADS 256
+#define BMPC_SCAN_ITEMS 4
+#define BMPC_SCAN_CHUNK (BMPC_SCAN_THREADS * BMPC_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t scan_xform(uint32_t x, uint32_t L) {
+    return L ? (x + L - 1u) / L : x;
+}
+
+// returns exclusive prefix of `v` across the block; total in *total (valid in all threads)
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[BMPC_SCAN_THREADS / 32];
+    __shared__ uint32_t block_total;
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < BMPC_SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
+        uint32_t winc = ws;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        if (lane < BMPC_SCAN_THREADS / 32) warp_sums[lane] = winc - ws;
+        if (lane == 31) block_total = winc;
+    }
+    __syncthreads();
+    uint32_t r = inc - v + warp_sums[wid];
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+scan_phase1_kernel(const uint32_t* in, uint32_t n, uint32_t L, uint32_t* chunk_sums) {
+    uint32_t base = blockIdx.x * BMPC_SCAN_CHUNK + threadIdx.x * BMPC_SCAN_ITEMS;
+    uint32_t s = 0;
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++)
+        if (base + j < n) s += scan_xform(in[base + j], L);
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+// single block: exclusive scan of chunk_sums in place; grand total -> chunk_sums[nchunks]
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+scan_phase2_kernel(uint32_t* chunk_sums, uint32_t nchunks) {
+    uint32_t carry = 0;
+    for (uint32_t start = 0; start < nchunks; start += BMPC_SCAN_THREADS) {
+        uint32_t idx = start + threadIdx.x;
+        uint32_t v = idx < nchunks ? chunk_sums[idx] : 0u;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (idx < nchunks) chunk_sums[idx] = ex + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) chunk_sums[nchunks] = carry;
+}
+// out has n + 1 entries; out[n] = grand total
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+scan_phase3_kernel(const uint32_t* in, uint32_t n, uint32_t L, const uint32_t* chunk_sums,
+                   uint32_t nchunks, uint32_t* out) {
+    uint32_t base = blockIdx.x * BMPC_SCAN_CHUNK + threadIdx.x * BMPC_SCAN_ITEMS;
+    uint32_t v[BMPC_SCAN_ITEMS];
+    uint32_t s = 0;
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++) {
+        v[j] = (base + j < n) ? scan_xform(in[base + j], L) : 0u;
+        s += v[j];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total) + chunk_sums[blockIdx.x];
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++) {
+        if (base + j < n) out[base + j] = ex;
+        ex += v[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = chunk_sums[nchunks];
+}
+
+// buckets whose points were split over more than one accumulate task
+__global__ void msm_find_heavy_kernel(const uint32_t* toff, uint32_t nb, uint32_t* heavy_list,
+                                      uint32_t* heavy_count) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    if (toff[b + 1] - toff[b] > 1u) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+}
+
+}  // namespace bmpc

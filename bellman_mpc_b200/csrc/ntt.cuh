@@ -1,0 +1,257 @@
+// Radix-2 Fr number-theoretic transform for EvaluationDomain::{fft, ifft, coset_fft,
+// icoset_fft} (reference: src/domain.rs:81-125, best_fft/serial_fft/parallel_fft :261-372).
+//
+// The reference bit-reverses and runs log n DIT stages over the whole vector (serial_fft) or
+// splits into 2^log_cpus sub-FFTs (parallel_fft).  Here the transform is a Stockham autosort
+// decomposition n = R_1 * R_2 * ... with R_j = 2^deg_j <= 2^10: one kernel launch per factor,
+// each block running all deg_j butterfly stages of T independent R_j-point sub-transforms out
+// of shared memory, so a 2^24 transform touches HBM 3 times instead of 24.  Natural order in,
+// natural order out (SURVEY 8a'/9) -- no separate bit-reversal pass.  The coset shift g^i,
+// the 1/m of the inverse transform and (for the prover) 1/Z are folded into the first pass's
+// loads / the last pass's stores (distribute_powers :101-113, ifft's minv loop :88-98,
+// divide_by_z_on_coset :139-151) instead of being separate sweeps over memory.
+//
+// Algorithmic traffic per transform: 64 B per coefficient (32 B read + 32 B write);
+// (m/2) log2 m butterflies of one Fr Montgomery product (136 MAC32) each.
+#pragma once
+#include "field.cuh"
+
+namespace bmpc {
+
+// x^e = hi[e >> lo_bits] * lo[e & mask]; a constant may be folded into every `lo` entry.
+struct PowTable {
+    const Fr* hi;
+    const Fr* lo;
+    uint32_t lo_bits;
+    uint32_t hi_n;  // entries in hi; 1 => lo alone covers the range
+};
+
+enum { SCALE_NONE = 0, SCALE_CONST = 1, SCALE_POW = 2 };
+
+struct NttPassArgs {
+    const Fr* in;
+    Fr* out;
+    uint32_t logn, deg, plog, tile_log;
+    PowTable tw;         // powers of omega_n (or its inverse)
+    const Fr* tw_small;  // powers of the 2^small_log-th root: tw_small[j], j < 2^(small_log-1)
+    uint32_t small_log;
+    int pre_mode, post_mode;
+    PowTable pre, post;
+    Fr post_const;
+};
+
+__device__ __forceinline__ Fr load_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_fr(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+__device__ __forceinline__ Fr pow_lookup(const PowTable& t, uint32_t e) {
+    Fr lo = ldg_fr(t.lo + (e & ((1u << t.lo_bits) - 1u)));
+    if (t.hi_n == 1) return lo;
+    return lo * ldg_fr(t.hi + (e >> t.lo_bits));
+}
+
+// One Stockham pass.  With t = n / R, p = 2^plog (product of the radices already done):
+//   for i in [0, t), k = i mod p:
+//     v[s]  = in[i + s t] * omega_n^{(t/p) k s}                 s in [0, R)
+//     V     = DFT_R(v)            (DIF stages in shared memory, read out bit-reversed)
+//     out[(i - k) R + k + s' p] = V[s']
+// Block = T consecutive i  x  R/2 butterflies; shared layout u[s][i_local].
+__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
+    extern __shared__ uint4 ntt_smem[];
+    Fr* u = reinterpret_cast<Fr*>(ntt_smem);
+    const uint32_t deg = A.deg, R = 1u << deg, T = 1u << A.tile_log;
+    const uint32_t tlog = A.logn - deg;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t il = tid & (T - 1u);
+    const uint32_t b = tid >> A.tile_log;
+    const uint32_t tile_base = blockIdx.x << A.tile_log;
+    const uint32_t i = tile_base + il;
+    const uint32_t pmask = (1u << A.plog) - 1u;
+    const uint32_t k = i & pmask;
+
+#pragma unroll 1
+    for (uint32_t h = 0; h < 2; h++) {
+        uint32_t s = b + h * (R >> 1);
+        uint32_t src = i + (s << tlog);
+        Fr v = load_fr(A.in + src);
+        if (A.pre_mode == SCALE_POW) v = v * pow_lookup(A.pre, src);
+        if (A.plog != 0) {
+            uint32_t e = (k * s) << (tlog - A.plog);
+            if (e != 0) v = v * pow_lookup(A.tw, e);
+        }
+        u[s * T + il] = v;
+    }
+    __syncthreads();
+
+    const uint32_t sshift = A.small_log - deg;
+#pragma unroll 1
+    for (uint32_t rnd = 0; rnd < deg; rnd++) {
+        uint32_t half = R >> (rnd + 1);
+        uint32_t di = b & (half - 1u);
+        uint32_t i0 = ((b - di) << 1) + di;
+        uint32_t i1 = i0 + half;
+        Fr x0 = u[i0 * T + il];
+        Fr x1 = u[i1 * T + il];
+        u[i0 * T + il] = x0 + x1;
+        Fr d = x0 - x1;
+        if (di != 0) d = d * ldg_fr(A.tw_small + ((di << rnd) << sshift));
+        u[i1 * T + il] = d;
+        __syncthreads();
+    }
+
+    const uint32_t half_threads = T << (deg - 1);  // == blockDim.x
+#pragma unroll 1
+    for (uint32_t h = 0; h < 2; h++) {
+        uint32_t sp, il2;
+        if (A.plog >= A.tile_log) {  // consecutive threads -> consecutive k: contiguous stores
+            il2 = il;
+            sp = b + h * (R >> 1);
+        } else {                      // first pass (p < T): consecutive threads -> consecutive s'
+            uint32_t o = tid + h * half_threads;
+            sp = o & (R - 1u);
+            il2 = o >> deg;
+        }
+        uint32_t i2 = tile_base + il2;
+        uint32_t k2 = i2 & pmask;
+        uint32_t dst = ((i2 - k2) << deg) + k2 + (sp << A.plog);
+        Fr v = u[(__brev(sp) >> (32u - deg)) * T + il2];
+        if (A.post_mode == SCALE_CONST) v = v * A.post_const;
+        else if (A.post_mode == SCALE_POW) v = v * pow_lookup(A.post, dst);
+        store_fr(A.out + dst, v);
+    }
+}
+
+// n == 1 transform: only the scalings apply.
+__global__ void ntt_trivial_kernel(NttPassArgs A) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        Fr v = load_fr(A.in);
+        if (A.pre_mode == SCALE_POW) v = v * pow_lookup(A.pre, 0);
+        if (A.post_mode == SCALE_CONST) v = v * A.post_const;
+        else if (A.post_mode == SCALE_POW) v = v * pow_lookup(A.post, 0);
+        store_fr(A.out, v);
+    }
+}
+
+// ------------------------------------------------------------------ setup kernels (tiny)
+// Domain constants for m = 2^logm (src/domain.rs:62-77,129-151), all Montgomery:
+//  [0] omega  [1] omega^-1  [2] m^-1  [3] g = 7  [4] g^-1  [5] (g^m - 1)^-1
+//  [6] m^-1 * (g^m - 1)^-1  [7] one  [8] omega_small  [9] omega_small^-1
+// root_of_unity = 7^((q-1)/2^32) (ff::PrimeField::root_of_unity for bls12_381::Scalar).
+__global__ void domain_consts_kernel(uint32_t logm, uint32_t small_log, Fr* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr root;  // Montgomery limbs of root_of_unity (oracle/fields.py self_check pins the value)
+    const uint32_t rl[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u,
+                            0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
+    for (int j = 0; j < 8; j++) root.l[j] = rl[j];
+    Fr omega = root;
+    for (uint32_t j = logm; j < 32; j++) omega = omega.sqr();
+    Fr osmall = root;
+    for (uint32_t j = small_log; j < 32; j++) osmall = osmall.sqr();
+    Fr one = Fr::one();
+    Fr seven = one;
+    for (int j = 0; j < 6; j++) seven = seven + one;
+    Fr m = one;
+    for (uint32_t j = 0; j < logm; j++) m = m.dbl();
+    Fr gm = seven;
+    for (uint32_t j = 0; j < logm; j++) gm = gm.sqr();
+    Fr zinv = (gm - one).inv();
+    Fr minv = m.inv();
+    out[0] = omega;
+    out[1] = omega.inv();
+    out[2] = minv;
+    out[3] = seven;
+    out[4] = seven.inv();
+    out[5] = zinv;
+    out[6] = minv * zinv;
+    out[7] = one;
+    out[8] = osmall;
+    out[9] = osmall.inv();
+}
+
+// out[j] = fold * base^(j * stride), j < count   (fold == NULL -> 1).  With canon != 0 the
+// entry is stored in canonical (non-Montgomery) form, so that a Montgomery product with it
+// both scales a coefficient and strips its Montgomery factor (to_le_bits for free).
+__global__ void pow_table_kernel(const Fr* base, const Fr* fold, uint64_t stride, uint32_t count,
+                                 int canon, Fr* out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Fr v = base->pow_u64((uint64_t)j * stride);
+    if (fold) v = v * *fold;
+    if (canon) v = v.from_mont();
+    out[j] = v;
+}
+// out[j] = a[j] * b[j] (tiny, for folding two constants)
+__global__ void fr_mul_kernel(const Fr* a, const Fr* b, Fr* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = *a * *b;
+}
+
+// ------------------------------------------------------------------- pointwise kernels
+// mul_assign (:154-170), sub_assign (:173-189), constant scaling (divide_by_z :139-151)
+__global__ void fr_mul_assign_kernel(Fr* a, const Fr* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr(a + i, load_fr(a + i) * load_fr(b + i));
+}
+__global__ void fr_sub_assign_kernel(Fr* a, const Fr* b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr(a + i, load_fr(a + i) - load_fr(b + i));
+}
+__global__ void fr_scale_kernel(Fr* a, const Fr* k, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Fr kk = *k;
+    if (i < n) store_fr(a + i, load_fr(a + i) * kk);
+}
+// a <- a * b - c  (prover.rs:221-224 mul_assign + sub_assign fused; 1/Z is folded into the
+// following icoset pass)
+__global__ void fr_mul_sub_kernel(Fr* a, const Fr* b, const Fr* c, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr(a + i, load_fr(a + i) * load_fr(b + i) - load_fr(c + i));
+}
+// distribute_powers(g) for an arbitrary g (:101-113): each thread owns CH consecutive
+// coefficients, starts from g^(first index) and keeps a running product like the reference's
+// per-chunk loop.
+__global__ void fr_distribute_powers_kernel(Fr* a, const Fr* g, size_t n) {
+    const int CH = 8;
+    size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CH;
+    if (first >= n) return;
+    Fr gg = *g;
+    Fr u = gg.pow_u64(first);
+    for (int j = 0; j < CH && first + j < n; j++) {
+        store_fr(a + first + j, load_fr(a + first + j) * u);
+        u = u * gg;
+    }
+}
+// Montgomery -> canonical little-endian (PrimeFieldBits::to_le_bits, prover.rs:231,241,248)
+__global__ void fr_to_canonical_kernel(Fr* a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr(a + i, load_fr(a + i).from_mont());
+}
+__global__ void fr_zero_kernel(Fr* a, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_fr(a + i, Fr::zero());
+}
+// tau^m - 1 (domain.rs:129-134)
+__global__ void fr_z_kernel(const Fr* tau, uint32_t logm, Fr* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr t = *tau;
+    for (uint32_t j = 0; j < logm; j++) t = t.sqr();
+    *out = t - Fr::one();
+}
+
+}  // namespace bmpc

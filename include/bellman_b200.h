@@ -1,0 +1,202 @@
+/* bellman_b200.h -- C ABI of libbellman_b200.so
+ *
+ * B200-native (sm_100a) replacement for the data-parallel hot path of
+ * doubiliu/bellman-mpc (a bellman 0.11.1 fork): Groth16 multiexp (MSM), the radix-2 Fr
+ * EvaluationDomain transforms, the H-polynomial pipeline + create_proof orchestration, and
+ * the ceremony's batch scalar multiplication.
+ *
+ * The reference has no FFI for this path (its only `extern "C"` precedent is the toy
+ * exports at src/lib.rs:156-164,179-201 on a crate-type = ["dylib"], Cargo.toml:48-50), so
+ * every entry point below cites the Rust function it replaces; INTEGRATION.md shows the
+ * `extern "C"` block + build.rs a maintainer adds to src/multiexp.rs, src/domain.rs and
+ * src/groth16/prover.rs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays little-endian u64/u32 limbs as Rust holds them
+ *   - scalars ("exponents"): canonical (non-Montgomery) 256-bit little-endian integers,
+ *     4 x u64 each == ff::FieldBits<[u64; 4]>                        (src/multiexp.rs:162)
+ *   - Fr coefficients: 4 x u64 Montgomery limbs, fully reduced == domain::Scalar<Fr>
+ *                                                                     (src/domain.rs:22,230)
+ *   - points in/out: ZCash uncompressed big-endian (G1 96 B, G2 192 B = x.c1|x.c0|y.c1|y.c0,
+ *     bit 0x40 of byte 0 = infinity) unless a "_mont" form is requested
+ *   - density maps: bitvec BitVec<Lsb0, usize> raw words, bit i = bit i%64 of word i/64
+ *                                                                     (src/multiexp.rs:117-157)
+ *   - every function returns a bmpc_status; there is NO CPU fallback: without a usable
+ *     CUDA device calls fail with BMPC_ERR_CUDA
+ *   - "_dev" variants take device pointers (inputs already resident in HBM) and a
+ *     cudaStream_t passed as void*; the plain variants take host pointers and include the
+ *     host<->device copies
+ */
+#ifndef BELLMAN_B200_H
+#define BELLMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bmpc_ctx bmpc_ctx;       /* one per process per GPU                         */
+typedef struct bmpc_bases bmpc_bases;   /* device-resident base vector (Arc<Vec<Affine>>)   */
+typedef struct bmpc_domain bmpc_domain; /* device-resident EvaluationDomain<Fr, Scalar<Fr>> */
+
+/* SynthesisError variants this path can produce (src/lib.rs:355-370) */
+typedef enum {
+    BMPC_OK = 0,
+    BMPC_ERR_UNEXPECTED_IDENTITY = 1,   /* SynthesisError::UnexpectedIdentity              */
+    BMPC_ERR_UNEXPECTED_EOF = 2,        /* SynthesisError::IoError(UnexpectedEof)          */
+    BMPC_ERR_DEGREE_TOO_LARGE = 3,      /* SynthesisError::PolynomialDegreeTooLarge        */
+    BMPC_ERR_LENGTH_MISMATCH = 4,       /* the reference's assert!/assert_eq! panics       */
+    BMPC_ERR_CUDA = 5,                  /* -> SynthesisError::IoError                      */
+    BMPC_ERR_INVALID = 6                /* malformed argument / encoding                   */
+} bmpc_status;
+
+enum { BMPC_G1 = 1, BMPC_G2 = 2 };
+/* point forms accepted by bmpc_bases_register */
+enum {
+    BMPC_FORM_UNCOMPRESSED_BE = 0,      /* G1Affine::to_uncompressed() bytes               */
+    BMPC_FORM_MONT_XY = 1               /* raw Montgomery limbs x|y, (0,0) == infinity     */
+};
+/* EvaluationDomain transforms (src/domain.rs:81-125) */
+enum { BMPC_FFT = 0, BMPC_IFFT = 1, BMPC_COSET_FFT = 2, BMPC_ICOSET_FFT = 3 };
+
+/* ---- context ------------------------------------------------------------------------ */
+/* replaces Worker::new() (src/multicore.rs:25-27): the execution resource handed to every call */
+int  bmpc_ctx_create(int device, bmpc_ctx** out);
+void bmpc_ctx_destroy(bmpc_ctx* ctx);
+const char* bmpc_last_error(const bmpc_ctx* ctx);
+/* tuning knobs (0 = automatic): MSM window bits, NTT max radix log2 */
+int  bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg);
+/* number of kernels launched by this context since creation (bench.py "gpu_launches") */
+uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx);
+
+/* ---- bases: SourceBuilder for (Arc<Vec<G>>, usize)  (src/multiexp.rs:45-86) -------------- */
+/* Upload a base vector once; the (handle, offset) pair passed to bmpc_multiexp is the
+ * reference's `(Arc<Vec<G::Affine>>, usize)` source (src/groth16/mod.rs:438-477). */
+int  bmpc_bases_register(bmpc_ctx* ctx, int group, const void* points, size_t n, size_t stride,
+                         int form, bmpc_bases** out);
+/* same, from a device array of Montgomery x|y points (copied) */
+int  bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont, size_t n,
+                             bmpc_bases** out, void* stream);
+size_t bmpc_bases_len(const bmpc_bases* b);
+int  bmpc_bases_group(const bmpc_bases* b);
+/* read points [start, start+count) back as uncompressed big-endian (tests / CRS export) */
+int  bmpc_bases_read(bmpc_ctx* ctx, const bmpc_bases* b, size_t start, size_t count, uint8_t* out);
+/* device pointer of the Montgomery x|y array (for harnesses that keep data resident) */
+const void* bmpc_bases_dev_ptr(const bmpc_bases* b);
+void bmpc_bases_free(bmpc_ctx* ctx, bmpc_bases* b);
+
+/* ---- multiexp  (src/multiexp.rs:254-281 `multiexp`, :159-250 `multiexp_inner`) ---------- */
+/* result = sum over dense positions k-th -> bases[base_offset + k] * scalars[position].
+ * density_words == NULL  <=> FullDensity; otherwise density_len must equal n
+ * (the reference's assert at :273-278 -> BMPC_ERR_LENGTH_MISMATCH).
+ * Error semantics follow SURVEY 8(a'): UNEXPECTED_EOF / UNEXPECTED_IDENTITY exactly when
+ * the reference's Source::{next,skip} would fail, same precedence (highest failing window of
+ * the reference's own window size, first error in scan order).
+ * out: 96 B (G1) / 192 B (G2) uncompressed affine of the sum (G::to_affine().to_uncompressed()). */
+int  bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                   const uint64_t* scalars, size_t n,
+                   const uint64_t* density_words, size_t density_len, uint8_t* out);
+int  bmpc_multiexp_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                       const uint64_t* d_scalars, size_t n,
+                       const uint64_t* d_density_words, size_t density_len,
+                       uint8_t* out, void* stream);
+/* Sharded form: same, but the result is left as this rank's partial sum in
+ * Montgomery XYZZ limbs (G1 192 B / G2 384 B) plus a status word; partials from all ranks are
+ * all-gathered by the host and folded with bmpc_sum_partials. */
+int  bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                               const uint64_t* d_scalars, size_t n,
+                               const uint64_t* d_density_words, size_t density_len,
+                               void* d_partial_out, void* stream);
+int  bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count,
+                       uint8_t* out, void* stream);
+size_t bmpc_partial_bytes(int group);
+
+/* ---- EvaluationDomain  (src/domain.rs:21-189) ------------------------------------------ */
+/* from_coeffs (:47-79): pads with zeros to m = 2^exp >= len (m = 1 for len <= 1);
+ * exp >= 32 -> BMPC_ERR_DEGREE_TOO_LARGE.  coeffs: len x 4 u64 Montgomery limbs (host). */
+int  bmpc_domain_from_coeffs(bmpc_ctx* ctx, const uint64_t* coeffs, size_t len, bmpc_domain** out);
+int  bmpc_domain_from_coeffs_dev(bmpc_ctx* ctx, const uint64_t* d_coeffs, size_t len,
+                                 bmpc_domain** out, void* stream);
+size_t   bmpc_domain_len(const bmpc_domain* d);      /* m          */
+uint32_t bmpc_domain_exp(const bmpc_domain* d);      /* log2 m     */
+/* into_coeffs (:43-45): copy the m coefficients back to the host */
+int  bmpc_domain_into_coeffs(bmpc_ctx* ctx, const bmpc_domain* d, uint64_t* out);
+uint64_t* bmpc_domain_dev_ptr(bmpc_domain* d);
+void bmpc_domain_free(bmpc_ctx* ctx, bmpc_domain* d);
+/* fft / ifft / coset_fft / icoset_fft (:81-125); op = BMPC_FFT ... */
+int  bmpc_domain_transform(bmpc_ctx* ctx, bmpc_domain* d, int op, void* stream);
+/* distribute_powers(g) (:101-113): coeffs[i] *= g^i ; g = 4 x u64 Montgomery */
+int  bmpc_domain_distribute_powers(bmpc_ctx* ctx, bmpc_domain* d, const uint64_t g[4], void* stream);
+/* z(tau) = tau^m - 1 (:129-134) ; tau/out Montgomery */
+int  bmpc_domain_z(bmpc_ctx* ctx, const bmpc_domain* d, const uint64_t tau[4], uint64_t out[4]);
+/* divide_by_z_on_coset (:139-151) */
+int  bmpc_domain_divide_by_z_on_coset(bmpc_ctx* ctx, bmpc_domain* d, void* stream);
+/* mul_assign / sub_assign (:154-189); length mismatch -> BMPC_ERR_LENGTH_MISMATCH */
+int  bmpc_domain_mul_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* other, void* stream);
+int  bmpc_domain_sub_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* other, void* stream);
+/* In-place transform of a caller-owned device array of m = 2^log_m Montgomery coefficients
+ * (harness entry point: inputs resident in HBM). */
+int  bmpc_ntt_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_m, int op, void* stream);
+/* Host-buffer convenience: upload, transform, download (what a drop-in `fft(&worker)` does). */
+int  bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op);
+
+/* ---- H polynomial  (src/groth16/prover.rs:210-231) -------------------------------------- */
+/* a, b, c: evaluations (len x 4 u64 Montgomery, host).  Runs 3 x (ifft, coset_fft),
+ * a*b - c, divide_by_z_on_coset, icoset_fft, drops the last coefficient and converts to
+ * canonical form (`to_le_bits`), fused on the device.  out: (m - 1) x 4 u64 canonical. */
+int  bmpc_h_coefficients(bmpc_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                         size_t len, uint64_t* out, size_t* out_len);
+/* device-resident form: d_a/d_b/d_c each hold m = 2^log_m coefficients (already padded) and
+ * are clobbered; the m-1 canonical scalars are left in d_a. */
+int  bmpc_h_coefficients_dev(bmpc_ctx* ctx, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c,
+                             uint32_t log_m, void* stream);
+/* Montgomery -> canonical (PrimeFieldBits::to_le_bits, prover.rs:231,241,248), in place */
+int  bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* stream);
+
+/* ---- create_proof  (src/groth16/prover.rs:176-350, everything after synthesis) ---------- */
+typedef struct {
+    /* ParameterSource for &Parameters (src/groth16/mod.rs:438-477) */
+    const bmpc_bases* h;
+    const bmpc_bases* l;
+    const bmpc_bases* a;
+    const bmpc_bases* b_g1;
+    const bmpc_bases* b_g2;
+    /* VerifyingKey parts the prover touches (prover.rs:309-327), uncompressed big-endian */
+    uint8_t alpha_g1[96];
+    uint8_t beta_g1[96];
+    uint8_t beta_g2[192];
+    uint8_t delta_g1[96];
+    uint8_t delta_g2[192];
+} bmpc_params;
+
+typedef struct {
+    /* ProvingAssignment after synthesis (prover.rs:55-69); Fr values are Montgomery limbs */
+    const uint64_t* a;  const uint64_t* b;  const uint64_t* c;   /* num_constraints x 4 */
+    size_t num_constraints;
+    const uint64_t* input_assignment;  size_t num_inputs;        /* x 4 */
+    const uint64_t* aux_assignment;    size_t num_aux;           /* x 4 */
+    const uint64_t* a_aux_density;     /* num_aux bits   */
+    const uint64_t* b_input_density;   /* num_inputs bits */
+    const uint64_t* b_aux_density;     /* num_aux bits   */
+} bmpc_assignment;
+
+/* r, s: 4 x u64 Montgomery.  proof_out: 192 B = A (G1 compressed) | B (G2 compressed) | C
+ * (Proof::write, src/groth16/mod.rs:42-48). */
+int  bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assignment* asg,
+                       const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
+/* ---- batch scalar multiplication  (src/groth16/mpc.rs:647-706 make_new_paramter /
+ *      make_new_tau_paramter; also fixed-base CRS synthesis, generator.rs:372-397,492-512) -- */
+/* out[i] = in[i] * k[i] (per_element = 1) or in[i] * k[0] (per_element = 0); k canonical 4 x u64 */
+int  bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* scalars,
+                           int per_element, bmpc_bases** out);
+/* out[i] = base * k[i]; base uncompressed big-endian; scalars canonical (host or device) */
+int  bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uint64_t* scalars,
+                         size_t n, int scalars_on_device, bmpc_bases** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELLMAN_B200_H */

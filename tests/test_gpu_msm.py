@@ -1,0 +1,212 @@
+"""GPU parity: multiexp vs the oracle restatement of src/multiexp.rs.
+`test_with_bls12` (multiexp.rs:283-327: naive sum == multiexp, FullDensity) is mirrored, and the
+semantics the reference never unit-tests directly -- density maps, base offsets, EOF / identity
+errors and their precedence (SURVEY 8a') -- are checked against `oracle.multiexp`."""
+import random
+
+import numpy as np
+import pytest
+
+import bellman_mpc_b200 as bm
+from oracle import curves, fields
+from oracle import multiexp as ome
+from util import Q, decode, expected_from_dlogs, known_dlog_bases, rand_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_points(group, ks):
+    G = curves.G1 if group == bm.G1 else curves.G2
+    return [G.mul(G.gen, k) if k else None for k in ks]
+
+
+def _run(worker, bases, start, density, scalars):
+    return bm.multiexp(worker, (bases, start), density, bm.ints_to_limbs(scalars)).wait()
+
+
+@pytest.mark.parametrize("group", [bm.G1, bm.G2])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 200])
+def test_with_bls12_small(worker, group, n):
+    """naive sum over oracle points == GPU multiexp == oracle multiexp (FullDensity)"""
+    G = curves.G1 if group == bm.G1 else curves.G2
+    ks = rand_scalars(n, 10 + n)
+    scalars = rand_scalars(n, 20 + n)
+    pts = _oracle_points(group, ks)
+    bases = bm.Bases.from_uncompressed(worker, group, b"".join(G.to_uncompressed(p) for p in pts))
+    got = _run(worker, bases, 0, bm.FullDensity(), scalars)
+    assert decode(group, got) == ome.naive(G, pts, scalars)
+    assert decode(group, got) == ome.multiexp(G, pts, 0, ome.FullDensity(), scalars)
+    # round trip of the resident copy (from_uncompressed -> Montgomery -> to_uncompressed)
+    assert bases.read() == b"".join(G.to_uncompressed(p) for p in pts)
+    bases.free()
+
+
+@pytest.mark.parametrize("group,n", [(bm.G1, 1 << 10), (bm.G1, 1 << 14), (bm.G2, 1 << 10)])
+@pytest.mark.parametrize("kind", ["uniform", "mixed", "small"])
+def test_known_dlog(worker, group, n, kind):
+    """bases with known discrete logs: expected = (sum k_i s_i) G, any size, no CPU MSM"""
+    ks = rand_scalars(n, 2)
+    scalars = rand_scalars(n, 1, kind)
+    bases = known_dlog_bases(worker, group, ks)
+    got = _run(worker, bases, 0, bm.FullDensity(), scalars)
+    assert got == expected_from_dlogs(group, ks, scalars)
+    bases.free()
+
+
+@pytest.mark.parametrize("c", [2, 5, 9, 13, 16])
+def test_window_independence(worker, c):
+    """SURVEY 8a'/7: the result does not depend on the window size"""
+    n = 3000
+    ks, scalars = rand_scalars(n, 3), rand_scalars(n, 4, "mixed")
+    bases = known_dlog_bases(worker, bm.G1, ks)
+    worker.set_tuning(c, 0)
+    try:
+        assert _run(worker, bases, 0, bm.FullDensity(), scalars) == expected_from_dlogs(bm.G1, ks, scalars)
+    finally:
+        worker.set_tuning(0, 0)
+    bases.free()
+
+
+@pytest.mark.parametrize("group", [bm.G1, bm.G2])
+def test_density_and_offset(worker, group):
+    """SURVEY 8a'/1: k-th dense exponent consumes base start + k"""
+    n, start = 777, 3
+    rng = random.Random(9)
+    bits = [rng.random() < 0.5 for _ in range(n)]
+    ks = rand_scalars(start + sum(bits) + 5, 5)          # bases may be longer than needed
+    scalars = rand_scalars(n, 6, "mixed")
+    bases = known_dlog_bases(worker, group, ks)
+    got = _run(worker, bases, start, bm.DensityTracker.from_bits(bits), scalars)
+    assert got == expected_from_dlogs(group, ks, scalars, bits, start)
+    # all-zero density: identity, nothing consumed even though start is past the end
+    none = bm.DensityTracker.from_bits([False] * n)
+    ident = _run(worker, bases, len(ks) + 10, none, scalars)
+    assert decode(group, ident) is None
+    bases.free()
+
+
+def test_duplicate_and_opposite_bases(worker):
+    """equal bases meet in one bucket (P + P) and opposite ones cancel (P + (-P))"""
+    G = curves.G1
+    n = 64
+    k = 123456789
+    ks = [k] * (n // 2) + [Q - k] * (n // 2)
+    scalars = [5] * n
+    bases = known_dlog_bases(worker, bm.G1, ks)
+    got = _run(worker, bases, 0, bm.FullDensity(), scalars)
+    assert decode(bm.G1, got) is None
+    scalars2 = [5] * (n // 2) + [0] * (n // 2)
+    got2 = _run(worker, bases, 0, bm.FullDensity(), scalars2)
+    assert decode(bm.G1, got2) == G.mul(G.gen, 5 * k * (n // 2) % Q)
+    bases.free()
+
+
+def test_empty(worker):
+    """SURVEY 8a'/8"""
+    bases = known_dlog_bases(worker, bm.G1, [1, 2, 3])
+    got = bm.multiexp(worker, (bases, 0), bm.FullDensity(), np.zeros((0, 4), dtype=np.uint64)).wait()
+    assert decode(bm.G1, got) is None
+    bases.free()
+
+
+def test_density_length_assert(worker):
+    """multiexp.rs:273-278"""
+    bases = known_dlog_bases(worker, bm.G1, [1, 2, 3])
+    with pytest.raises(AssertionError):
+        bm.multiexp(worker, (bases, 0), bm.DensityTracker.from_bits([True, True]), bm.ints_to_limbs([1, 2, 3]))
+    bases.free()
+
+
+def _error_case(worker, pts, start, bits, scalars):
+    """run GPU and oracle on the same case; both must agree on value or error class"""
+    G = curves.G1
+    bases = bm.Bases.from_uncompressed(worker, bm.G1, b"".join(G.to_uncompressed(p) for p in pts))
+    dens_g = bm.FullDensity() if bits is None else bm.DensityTracker.from_bits(bits)
+    dens_o = ome.FullDensity()
+    if bits is not None:
+        dens_o = ome.DensityTracker()
+        dens_o.bv = list(bits)
+    try:
+        exp = ("ok", ome.multiexp(G, pts, start, dens_o, scalars))
+    except ome.UnexpectedIdentity:
+        exp = ("identity", None)
+    except ome.UnexpectedEof:
+        exp = ("eof", None)
+    try:
+        got = ("ok", decode(bm.G1, _run(worker, bases, start, dens_g, scalars)))
+    except bm.UnexpectedIdentity:
+        got = ("identity", None)
+    except bm.UnexpectedEof:
+        got = ("eof", None)
+    bases.free()
+    assert got == exp, (got[0], exp[0])
+    return exp[0]
+
+
+def test_error_semantics(worker):
+    """SURVEY 8a'/3-5 (multiexp.rs:55-65,74-80,244-249)"""
+    G = curves.G1
+    rng = random.Random(77)
+    n = 40                                   # reference window c = ceil(ln 40) = 4
+    pts = [G.mul(G.gen, rng.randrange(1, Q)) for _ in range(n)]
+    sc = [rng.randrange(Q) for _ in range(n)]
+    # identity base under a zero scalar: fine
+    p1 = list(pts); p1[7] = None
+    s1 = list(sc); s1[7] = 0
+    assert _error_case(worker, p1, 0, None, s1) == "ok"
+    # identity under a non-zero scalar: UnexpectedIdentity
+    assert _error_case(worker, p1, 0, None, sc) == "identity"
+    # identity under density-0 position: fine (never consumed)
+    bits = [True] * n; bits[7] = False
+    p2 = list(pts); p2[n - 1] = None         # only 39 dense positions: base 39 is never consumed
+    assert _error_case(worker, p2, 0, bits, sc) == "ok"
+    # bases run out: EOF, also when the overrunning scalars are zero
+    assert _error_case(worker, pts[:30], 0, None, sc) == "eof"
+    s3 = list(sc)
+    for i in range(30, n):
+        s3[i] = 0
+    assert _error_case(worker, pts[:30], 0, None, s3) == "eof"
+    # start offset past the end with dense positions
+    assert _error_case(worker, pts, n, None, sc) == "eof"
+    # EOF + earlier identity whose top-window digit is zero -> EOF wins; non-zero -> identity wins
+    p4 = list(pts[:30]); p4[3] = None
+    s4 = list(sc); s4[3] = 5                 # small scalar: top window (bits 252..255) digit is 0
+    assert _error_case(worker, p4, 0, None, s4) == "eof"
+    s5 = list(sc); s5[3] = (1 << 253) + 9    # top-window digit non-zero
+    assert _error_case(worker, p4, 0, None, s5) == "identity"
+    # scalar == 1 on an identity base is consumed (window 0) -> identity error
+    s6 = list(sc); s6[7] = 1
+    assert _error_case(worker, p1, 0, None, s6) == "identity"
+
+
+def test_batch_scalar_mul(worker):
+    """mpc.rs:647-706: per-element and same-scalar batch multiplication, G1 and G2"""
+    for group in (bm.G1, bm.G2):
+        G = curves.G1 if group == bm.G1 else curves.G2
+        ks = rand_scalars(50, 31)
+        mult = rand_scalars(50, 32)
+        mult[3] = 0
+        bases = known_dlog_bases(worker, group, ks)
+        per = bases.scalar_mul(bm.ints_to_limbs(mult), per_element=True)
+        exp = b"".join(G.to_uncompressed(G.mul(G.gen, k * m % Q)) for k, m in zip(ks, mult))
+        assert per.read() == exp
+        same = bases.scalar_mul(bm.ints_to_limbs([mult[0]]), per_element=False)
+        exp2 = b"".join(G.to_uncompressed(G.mul(G.gen, k * mult[0] % Q)) for k in ks)
+        assert same.read() == exp2
+        for b in (bases, per, same):
+            b.free()
+
+
+def test_large_known_dlog(worker):
+    """config #2: G1 multiexp 2^20, uniform scalars, known-dlog bases, FullDensity"""
+    n = 1 << 20
+    rs = np.random.RandomState(1)
+    ks_l = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    sc_l = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    G = curves.G1
+    bases = bm.Bases.fixed_base_mul(worker, bm.G1, G.to_uncompressed(G.gen), ks_l)
+    got = bm.multiexp(worker, (bases, 0), bm.FullDensity(), sc_l).wait()
+    ks, sc = bm.limbs_to_ints(ks_l), bm.limbs_to_ints(sc_l)
+    dot = sum(k * s for k, s in zip(ks, sc)) % Q
+    assert got == G.to_uncompressed(G.mul(G.gen, dot))
+    bases.free()

@@ -1,0 +1,76 @@
+"""GPU parity: create_proof (src/groth16/prover.rs:176-350) on the reference's own demo
+circuits, checked byte-for-byte against the oracle restatement and against the
+known-trapdoor expectation."""
+import random
+
+import numpy as np
+import pytest
+
+import bellman_mpc_b200 as bm
+from oracle import curves, fields
+from oracle import groth16 as og
+
+pytestmark = pytest.mark.gpu
+F = fields.Fr
+Q = F.p
+
+
+def upload_params(worker, params):
+    G1, G2 = curves.G1, curves.G2
+    up1 = lambda v: bm.Bases.from_uncompressed(worker, bm.G1, b"".join(G1.to_uncompressed(p) for p in v), len(v))
+    up2 = lambda v: bm.Bases.from_uncompressed(worker, bm.G2, b"".join(G2.to_uncompressed(p) for p in v), len(v))
+    vk = params.vk
+    return bm.Parameters(worker, up1(params.h), up1(params.l), up1(params.a), up1(params.b_g1), up2(params.b_g2),
+                         G1.to_uncompressed(vk.alpha_g1), G1.to_uncompressed(vk.beta_g1),
+                         G2.to_uncompressed(vk.beta_g2), G1.to_uncompressed(vk.delta_g1),
+                         G2.to_uncompressed(vk.delta_g2))
+
+
+def to_gpu_assignment(prover):
+    dens = lambda d: bm.DensityTracker.from_bits(d.bv)
+    return bm.ProvingAssignment(bm.fr_to_mont(prover.a), bm.fr_to_mont(prover.b), bm.fr_to_mont(prover.c),
+                                bm.fr_to_mont(prover.input_assignment), bm.fr_to_mont(prover.aux_assignment),
+                                dens(prover.a_aux_density), dens(prover.b_input_density),
+                                dens(prover.b_aux_density))
+
+
+def test_xor_demo(worker):
+    """groth16/tests/mod.rs XorDemo on BLS12-381 with the fork's fixed toxic waste and r, s"""
+    E = og.BLS12
+    params = og.generate_random_parameters(E, og.xor_demo(None, None))
+    gp = upload_params(worker, params)
+    for a, b in [(False, False), (True, False), (True, True)]:
+        prover = og.synthesize_for_proving(E, og.xor_demo(a, b))
+        proof = bm.create_random_proof(to_gpu_assignment(prover), gp)
+        assert len(proof) == 192
+        assert proof == og.create_proof_from_assignment(E, prover, params, 27134, 17146).to_bytes(E)
+        assert proof == og.expected_proof(E, params, prover, 27134, 17146).to_bytes(E)
+
+
+def test_mimc(worker):
+    """config #1: the crate's MiMC circuit (src/mimc_mod.rs; 646 constraints -> domain 1024,
+    MSM sizes 1023 / 645 / 2), proof bytes == known-trapdoor proof"""
+    E = og.BLS12
+    rng = random.Random(2024)
+    constants = [rng.randrange(Q) for _ in range(og.MIMC_ROUNDS)]
+    xl, xr = rng.randrange(Q), rng.randrange(Q)
+    params = og.generate_random_parameters(E, og.mimc_demo(F, None, None, constants))
+    assert len(params.h) == 1023 and len(params.l) == 645
+    gp = upload_params(worker, params)
+    prover = og.synthesize_for_proving(E, og.mimc_demo(F, xl, xr, constants))
+    assert prover.input_assignment[1] == og.mimc(F, xl, xr, constants)
+    assert prover.a_aux_density.get_total_density() == 644
+    assert prover.b_aux_density.get_total_density() == 322
+    proof = bm.create_random_proof(to_gpu_assignment(prover), gp)
+    assert proof == og.expected_proof(E, params, prover, 27134, 17146).to_bytes(E)
+
+
+def test_delta_identity_rejected(worker):
+    """prover.rs:309-313 subversion check"""
+    E = og.BLS12
+    params = og.generate_random_parameters(E, og.xor_demo(None, None))
+    gp = upload_params(worker, params)
+    gp.delta_g1 = curves.G1.to_uncompressed(None)
+    prover = og.synthesize_for_proving(E, og.xor_demo(True, False))
+    with pytest.raises(bm.UnexpectedIdentity):
+        bm.create_random_proof(to_gpu_assignment(prover), gp)
