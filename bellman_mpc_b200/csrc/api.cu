@@ -123,6 +123,35 @@ int bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg) {
 
 uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int bmpc_ctx_profile(bmpc_ctx* ctx, int enable) {
+    if (!ctx) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profile = enable != 0;
+    return BMPC_OK;
+}
+
+int bmpc_ctx_profile_read(bmpc_ctx* ctx, int which, double* ms_total, uint64_t* launches) {
+    if (!ctx || which < 0 || which >= BMPC_PROF_COUNT) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    CK(cudaDeviceSynchronize());
+    for (auto& ev : ctx->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev.e0, ev.e1) == cudaSuccess) {
+            ctx->prof_ms[ev.id] += ms;
+            ctx->prof_n[ev.id] += 1;
+        }
+        cudaEventDestroy(ev.e0);
+        cudaEventDestroy(ev.e1);
+    }
+    ctx->prof_pending.clear();
+    if (ms_total) *ms_total = ctx->prof_ms[which];
+    if (launches) *launches = ctx->prof_n[which];
+    ctx->prof_ms[which] = 0;
+    ctx->prof_n[which] = 0;
+    return BMPC_OK;
+}
+
 // ---------------------------------------------------------------------------- bases
 int bmpc_bases_register(bmpc_ctx* ctx, int group, const void* points, size_t n, size_t stride,
                         int form, bmpc_bases** out) {

@@ -23,7 +23,11 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     }
     const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
     uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
-    LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.off, s.toff, p.nb, g.L, partials);
+    {
+        ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
+        LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.off, s.toff, p.nb, g.L, partials);
+    }
+    ProfScope ps_tail(ctx, BMPC_PROF_MSM_REDUCE, st);
     {
         size_t smem = 128 * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_combine_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

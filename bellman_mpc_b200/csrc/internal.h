@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "curve.cuh"
 
@@ -50,6 +51,12 @@ struct bmpc_ctx {
     uint8_t* d_stage = nullptr;  // 4 KB
     std::map<uint32_t, bmpc::DomainTables> domains;
     bmpc::Fr* tw_small[2] = {nullptr, nullptr};  // fwd / inv powers of the 2^SMALL_LOG-th root
+    // optional per-kernel timing (bench.py roofline): CUDA event pairs on the launching stream
+    bool profile = false;
+    struct ProfEvent { int id; cudaEvent_t e0, e1; };
+    std::vector<ProfEvent> prof_pending;
+    double prof_ms[BMPC_PROF_COUNT] = {0};
+    uint64_t prof_n[BMPC_PROF_COUNT] = {0};
 };
 
 struct bmpc_bases {
@@ -96,6 +103,26 @@ struct DeviceGuard {
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// RAII event pair around one kernel launch (only when profiling is on)
+struct ProfScope {
+    bmpc_ctx* ctx;
+    cudaStream_t st;
+    bmpc_ctx::ProfEvent ev;
+    bool on;
+    ProfScope(bmpc_ctx* c, int id, cudaStream_t s) : ctx(c), st(s), on(c->profile) {
+        if (!on) return;
+        ev.id = id;
+        cudaEventCreate(&ev.e0);
+        cudaEventCreate(&ev.e1);
+        cudaEventRecord(ev.e0, st);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(ev.e1, st);
+        ctx->prof_pending.push_back(ev);
     }
 };
 

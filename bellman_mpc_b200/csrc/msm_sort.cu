@@ -69,6 +69,7 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
                  const uint32_t* d_scalars, size_t n, const uint32_t* d_density, uint32_t* d_flags,
                  MsmSorted* out, cudaStream_t st) {
     const MsmGeom& g = p.g;
+    ProfScope ps(ctx, BMPC_PROF_MSM_SORT, st);
     MsmInput in;
     in.scalars = d_scalars;
     in.n = n;

@@ -143,7 +143,10 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
         uint32_t threads = 1u << (tile_log + deg - 1);
         uint32_t blocks = 1u << (tlog - tile_log);
         size_t smem = ((size_t)1 << (tile_log + deg)) * sizeof(Fr);
-        LAUNCH(ctx, ntt_pass_kernel, blocks, threads, smem, st, A);
+        {
+            ProfScope ps(ctx, BMPC_PROF_NTT_PASS, st);
+            LAUNCH(ctx, ntt_pass_kernel, blocks, threads, smem, st, A);
+        }
         src = dst;
         plog += deg;
     }

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Groth16 hot path on B200.
+
+Metric (BASELINE.json): G1 MSM Mpts/s @ 2^24 at 1/2/4/8 B200 (the scaling metric; `value`),
+with Groth16 prove seconds @ 2^22 constraints reported in the same line under "prove" (N = 1).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+One "step" = one multiexp over the whole 2^24-point workload (strong scaling: the bases are
+split across the N ranks, each rank reduces its slice to a partial sum, the 192-byte partials
+are all-gathered over NCCL and folded on every rank).  Inputs are resident in HBM for `value`;
+`e2e` times the host-buffer C-ABI call (pinned host scalars -> H2D inside the timed region,
+result bytes D2H).  Bases are the CRS: registered once, resident, like `Parameters` in a prover.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "g1_msm_mpts_per_s_2p24"
+UNIT = "Mpts/s"
+G1_MSM_BYTES_PER_POINT = 128        # 96 B affine base + 32 B scalar
+G1_MSM_MAC32_PER_POINT = 48_000     # 16 windows x 10 Fp mul x 300 MAC32
+G2_MSM_MAC32_PER_POINT = 144_000
+
+
+def rand_limbs(n, seed):
+    """n x 4 u64, uniform below 2^254 (< q): canonical scalars"""
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 1 << 63, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    a[:, 3] >>= np.uint64(1)
+    return a
+
+
+def measured_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            peaks["source"] = "measured"
+        except Exception:
+            pass
+    ip = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
+    if os.path.exists(ip):
+        try:
+            peaks["mac32_per_s"] = float(json.load(open(ip))["cc_pair_mac32_per_s"])
+        except Exception:
+            pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU restatement of the reference's multiexp (oracle/c, pthreads, one task per window as
+    multiexp.rs:238-242) on all host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import ctypes as C
+
+    from oracle import cref
+    lib = cref.load()
+    lib.orc_bases_g1_sequence.restype = C.c_void_p
+    lib.orc_bases_g1_sequence.argtypes = [C.c_size_t, C.c_uint64]
+    threads = cref.hardware_threads()
+    sample_log = args.ref_sample_log
+    n = 1 << sample_log
+    bases = cref.CBases(1, lib.orc_bases_g1_sequence(n, 1))
+    scalars = rand_limbs(n, 1)
+    for _ in range(args.warmup):
+        cref.multiexp(bases, 0, scalars, threads=threads)
+    t0 = time.perf_counter()
+    out = None
+    for _ in range(args.steps):
+        st, out = cref.multiexp(bases, 0, scalars, threads=threads)
+        assert st == 0
+    dt = (time.perf_counter() - t0) / args.steps
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
+    ok = out == cref.g1_generator_mul(cref.fr_dot(ks, scalars))
+    value = n / dt / 1e6
+    sample = f"G1 multiexp over a 2^{sample_log}-point sample of the 2^{args.log_n} workload, window c={lib.orc_window_size(n)}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64-limb Montgomery (CPU)", "data": "synthetic",
+        "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity",
+                   "bases": "k_i*G (known discrete logs)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "result_checked": bool(ok)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import bellman_mpc_b200 as bm
+    from bellman_mpc_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = bm.Worker(local)
+    lib = w._lib
+    stream = torch.cuda.current_stream().cuda_stream
+
+    n_total = 1 << args.log_n
+    n = n_total // world
+    curves_gen = bytes.fromhex(
+        "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+        "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1")
+    ks = rand_limbs(n, 2 + 7919 * rank)
+    t_setup = time.perf_counter()
+    bases = bm.Bases.fixed_base_mul(w, bm.G1, curves_gen, ks)          # resident CRS slice, k_i * G
+    scalars_h = torch.from_numpy(rand_limbs(n, 1 + 7919 * rank).view(np.int64)).pin_memory()
+    scalars_d = scalars_h.to(dev)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    pbytes = int(lib.bmpc_partial_bytes(bm.G1))
+    partial = torch.zeros(pbytes, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * pbytes, dtype=torch.uint8, device=dev)
+    out = np.zeros(96, dtype=np.uint8)
+    import ctypes as C
+    optr = out.ctypes.data_as(C.c_void_p)
+
+    def step_resident(sc_ptr):
+        if world == 1:
+            st = lib.bmpc_multiexp_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, optr, stream)
+        else:
+            st = lib.bmpc_multiexp_partial_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, partial.data_ptr(), stream)
+            assert st == 0, st
+            dist.all_gather_into_tensor(gathered, partial)
+            st = lib.bmpc_sum_partials(w.ctx, bm.G1, gathered.data_ptr(), world, optr, stream)
+        assert st == 0, (st, lib.bmpc_last_error(w.ctx))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- device-resident timing (value) with per-kernel events for the roofline
+    for _ in range(args.warmup):
+        step_resident(scalars_d.data_ptr())
+    lib.bmpc_ctx_profile(w.ctx, 1)
+    launches0 = w.launch_count()
+    with ClockSampler(local) as clocks:
+        ms = timed(lambda: step_resident(scalars_d.data_ptr()), args.steps)
+    launches = w.launch_count() - launches0
+    prof = {}
+    for name, pid in (("accumulate", 0), ("sort", 2), ("reduce", 3)):
+        t_ms, cnt = C.c_double(), C.c_uint64()
+        lib.bmpc_ctx_profile_read(w.ctx, pid, C.byref(t_ms), C.byref(cnt))
+        prof[name] = (t_ms.value / max(cnt.value, 1), int(cnt.value))
+    lib.bmpc_ctx_profile(w.ctx, 0)
+    result_resident = out.tobytes()
+    value = n_total / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer call
+    def step_e2e():
+        if world == 1:
+            st = lib.bmpc_multiexp(w.ctx, bases.handle, 0, scalars_h.data_ptr(), n, None, 0, optr)
+            assert st == 0, st
+        else:
+            scalars_d.copy_(scalars_h, non_blocking=True)
+            step_resident(scalars_d.data_ptr())
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms_dev = timed(step_e2e, args.steps)
+    e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max(e2e_ms_dev, 0.0) if world > 1 else e2e_wall   # host call is synchronous: wall == device + copies
+    if world > 1:
+        t = torch.tensor([e2e_wall], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    assert out.tobytes() == result_resident
+
+    peaks = measured_peaks()
+    acc_ms, acc_cnt = prof["accumulate"]
+    roofline = {
+        "kernel": "msm_accumulate_kernel<Fp>", "bound": "hbm",
+        "achieved": G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": (G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
+        "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
+        "kernel_ms": acc_ms, "share_of_step": acc_ms / ms if ms else None,
+        "note": "integer-pipe bound, not HBM bound: see roofline_int",
+    }
+    roofline_int = None
+    if peaks.get("mac32_per_s") and acc_ms:
+        ach = G1_MSM_MAC32_PER_POINT * n / (acc_ms * 1e-3)
+        roofline_int = {"kernel": "msm_accumulate_kernel<Fp>", "bound": "int32-mac",
+                        "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12, "unit": "TMAC32/s",
+                        "frac": ach / peaks["mac32_per_s"],
+                        "peak_source": "profiles/r01_imad_peak.json (mad.lo.cc/madc.hi.cc chains, measured)",
+                        "model": "48000 MAC32 per point (SURVEY 8d: 16 windows x 10 Fp mul x 300)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32-limb Montgomery (Fp 12x32, Fr 8x32)", "data": "synthetic",
+        "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity "
+                               f"(BASELINE configs[1] shape at the size the metric is quoted on)",
+                   "bases": "k_i*G, resident (CRS registered once)", "points_per_gpu": n,
+                   "l2": "inputs larger than L2 (scalars %d MiB + bases %d MiB per GPU)" % (n * 32 >> 20, n * 96 >> 20),
+                   "parallelism": f"bases split x{world}, all-gather of {pbytes}-byte partials" if world > 1 else "single GPU",
+                   "setup_s": round(t_setup, 2)},
+        "clocks": clocks.summary(),
+        "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96 + 64},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_int": roofline_int,
+        "kernel_ms": {k: v[0] for k, v in prof.items()},
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1): oracle on a bounded sample + parity check
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cref
+        threads = cref.hardware_threads()
+        slog = args.ref_sample_log
+        ns = 1 << slog
+        cb = cref.CBases.from_uncompressed(1, bases.read(0, ns))
+        sc = np.ascontiguousarray(scalars_h.numpy().view(np.uint64)[:ns])
+        t0 = time.perf_counter()
+        st, cpu_out = cref.multiexp(cb, 0, sc, threads=threads)
+        cpu_s = time.perf_counter() - t0
+        gpu_out = bm.multiexp(w, (bases, 0), bm.FullDensity(), sc).wait()
+        line["cpu_baseline"] = {"value": ns / cpu_s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"first 2^{slog} points of the workload, reference window c={cref.load().orc_window_size(ns)}",
+                                "seconds": cpu_s, "matches_gpu_bytes": bool(st == 0 and cpu_out == gpu_out)}
+        cb.free()
+
+    # ---- Groth16 prove @ 2^prove_log_n (N = 1), same run
+    if world == 1 and not args.no_prove:
+        try:
+            from bench_prove import prove_bench
+            line["prove"] = prove_bench(w, args.prove_log_n, max(2, args.steps // 2), args.no_cpu_baseline)
+        except Exception as e:  # keep the headline line even if the secondary workload fails
+            line["prove"] = {"error": repr(e)}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    bases.free()
+    w.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--ref-sample-log", type=int, default=18)
+    ap.add_argument("--prove-log-n", type=int, default=22)
+    ap.add_argument("--no-prove", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,14 @@ int  bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx);
 
+/* Per-kernel device timing for the roofline report: when enabled, the named kernels are
+ * bracketed by CUDA events on their launching stream.  bmpc_ctx_profile_read synchronises,
+ * returns the accumulated milliseconds / launch count for `which` and resets them. */
+enum { BMPC_PROF_MSM_ACCUMULATE = 0, BMPC_PROF_NTT_PASS = 1, BMPC_PROF_MSM_SORT = 2,
+       BMPC_PROF_MSM_REDUCE = 3, BMPC_PROF_COUNT = 4 };
+int  bmpc_ctx_profile(bmpc_ctx* ctx, int enable);
+int  bmpc_ctx_profile_read(bmpc_ctx* ctx, int which, double* ms_total, uint64_t* launches);
+
 /* ---- bases: SourceBuilder for (Arc<Vec<G>>, usize)  (src/multiexp.rs:45-86) -------------- */
 /* Upload a base vector once; the (handle, offset) pair passed to bmpc_multiexp is the
  * reference's `(Arc<Vec<G::Affine>>, usize)` source (src/groth16/mod.rs:438-477). */

@@ -68,6 +68,12 @@ static inline void fp2_mul_3b(fp2_t* r, const fp2_t* a) { /* 3b = 12 (1 + u) on 
 #undef GP_
 #undef MUL_3B
 
+/* G1 generator, Montgomery limbs (y checked by tests/test_oracle_c.py) */
+static const uint64_t G1_GEN_X[6] = {0x5cb38790fd530c16ULL, 0x7817fc679976fff5ULL, 0x154f95c7143ba1c1ULL,
+                                     0xf0ae6acdf3d0e747ULL, 0xedce6ecc21dbf440ULL, 0x120177419e0bfb75ULL};
+static const uint64_t G1_GEN_Y[6] = {0xbaac93d50ce72271ULL, 0x8c22631a7918fd8eULL, 0xdd595f13570725ceULL,
+                                     0x51ac582950405194ULL, 0x0e1c8c3fad0059c0ULL, 0x0bbc3efc5008a26aULL};
+
 /* ------------------------------------------------------------------------- tiny task pool
  * rayon stand-in: run `count` independent tasks on up to `threads` OS threads. */
 typedef void (*task_fn)(void* arg, size_t idx);
@@ -238,6 +244,39 @@ orc_bases_t* orc_bases_from_mont(int group, const uint64_t* data, size_t n) {
     }
     return b;
 }
+/* Synthetic G1 bases with known discrete logs for the CPU-only reference arm of bench.py:
+ * P_i = (first + i) * G, built by repeated mixed addition and one batch inversion. */
+orc_bases_t* orc_bases_g1_sequence(size_t n, uint64_t first) {
+    orc_bases_t* b = (orc_bases_t*)malloc(sizeof(*b));
+    b->group = 1; b->n = n;
+    g1_affine_t* out = (g1_affine_t*)malloc((n ? n : 1) * sizeof(g1_affine_t));
+    b->pts = out;
+    if (!n) return b;
+    g1_affine_t gen; memcpy(gen.x.l, G1_GEN_X, 48); memcpy(gen.y.l, G1_GEN_Y, 48); gen.inf = 0;
+    g1_t g, cur; g1_from_affine(&g, &gen);
+    uint64_t k[4] = {first, 0, 0, 0};
+    g1_mul(&cur, &g, k);
+    g1_t* proj = (g1_t*)malloc(n * sizeof(g1_t));
+    fp_t* pre = (fp_t*)malloc(n * sizeof(fp_t));
+    fp_t acc; fp_one(&acc);
+    for (size_t i = 0; i < n; i++) {
+        proj[i] = cur;
+        pre[i] = acc;
+        if (!g1_is_identity(&cur)) fp_mul(&acc, &acc, &cur.z);
+        g1_add_mixed(&cur, &cur, &gen);
+    }
+    fp_t inv; fp_inv(&inv, &acc);
+    for (size_t i = n; i-- > 0;) {
+        if (g1_is_identity(&proj[i])) { fp_zero(&out[i].x); fp_zero(&out[i].y); out[i].inf = 1; continue; }
+        fp_t zi; fp_mul(&zi, &inv, &pre[i]);
+        fp_mul(&inv, &inv, &proj[i].z);
+        fp_mul(&out[i].x, &proj[i].x, &zi);
+        fp_mul(&out[i].y, &proj[i].y, &zi);
+        out[i].inf = 0;
+    }
+    free(proj); free(pre);
+    return b;
+}
 void orc_bases_free(orc_bases_t* b) { if (b) { free(b->pts); free(b); } }
 size_t orc_bases_len(const orc_bases_t* b) { return b->n; }
 
@@ -279,10 +318,6 @@ int orc_naive_multiexp(const orc_bases_t* b, const uint64_t* exps, size_t n, uin
 }
 
 /* generator * k as uncompressed bytes, and sum_i k_i * s_i mod q (known-dlog expectations) */
-static const uint64_t G1_GEN_X[6] = {0x5cb38790fd530c16ULL, 0x7817fc679976fff5ULL, 0x154f95c7143ba1c1ULL,
-                                     0xf0ae6acdf3d0e747ULL, 0xedce6ecc21dbf440ULL, 0x120177419e0bfb75ULL};
-static const uint64_t G1_GEN_Y[6] = {0xbaac93d50ce72271ULL, 0x8c22631a7918fd8eULL, 0xdd595f13570725ceULL,
-                                     0x51ac582950405194ULL, 0x0e1c8c3fad0059c0ULL, 0x0bbc3efc5008a26aULL};
 void orc_g1_generator_mul(const uint64_t k[4], uint8_t out[96]) {
     g1_t g, r; g1_affine_t a;
     memcpy(g.x.l, G1_GEN_X, 48); memcpy(g.y.l, G1_GEN_Y, 48); fp_one(&g.z);

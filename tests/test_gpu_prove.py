@@ -74,3 +74,19 @@ def test_delta_identity_rejected(worker):
     prover = og.synthesize_for_proving(E, og.xor_demo(True, False))
     with pytest.raises(bm.UnexpectedIdentity):
         bm.create_random_proof(to_gpu_assignment(prover), gp)
+
+
+@pytest.mark.parametrize("log_m,profile", [(5, "uniform"), (12, "uniform"), (14, "boolean")])
+def test_synthetic_prove_known_dlog_and_cpu(worker, log_m, profile):
+    """config #4 at test sizes: synthetic R1CS state with random densities and a known-dlog CRS.
+    GPU proof == known-dlog expectation == C restatement of prover.rs:206-350."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench_prove import Workload
+    from oracle import cref
+    wl = Workload(worker, log_m, seed=40 + log_m, profile=profile)
+    proof = wl.prove()
+    assert proof == wl.expected_proof()
+    st, cpu_proof, _ = wl.cpu_reference_proof(threads=4)
+    assert st == 0 and cpu_proof == proof
+    wl.free()
