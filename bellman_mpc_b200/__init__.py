@@ -225,36 +225,53 @@ class FullDensity:
 
 
 class DensityTracker:
-    """multiexp.rs:116-157"""
+    """multiexp.rs:116-157.  Bits are kept in a numpy array; `words()` is the raw
+    BitVec<Lsb0, usize> storage handed to the C ABI (cached until the next mutation)."""
 
     def __init__(self):
-        self.bv = []
+        self._bits = np.zeros(0, dtype=bool)
+        self._n = 0
+        self._words = None
+
+    @property
+    def bv(self):
+        return self._bits[: self._n]
 
     def add_element(self):
-        self.bv.append(False)
+        if self._n == self._bits.size:
+            grown = np.zeros(max(64, 2 * self._bits.size), dtype=bool)
+            grown[: self._n] = self._bits[: self._n]
+            self._bits = grown
+        self._bits[self._n] = False
+        self._n += 1
+        self._words = None
 
     def inc(self, idx):
-        self.bv[idx] = True
+        if idx >= self._n:
+            raise IndexError(idx)
+        self._bits[idx] = True
+        self._words = None
 
     def get_total_density(self):
-        return int(sum(self.bv))
+        return int(self.bv.sum())
 
     def get_query_size(self):
-        return len(self.bv)
+        return self._n
 
     def words(self):
-        bits = np.asarray(self.bv, dtype=np.uint8)
-        pad = (-len(bits)) % 64
-        if pad:
-            bits = np.concatenate([bits, np.zeros(pad, dtype=np.uint8)])
-        if len(bits) == 0:
-            return np.zeros(1, dtype=np.uint64)
-        return np.packbits(bits, bitorder="little").view(np.uint64).copy()
+        if self._words is None:
+            bits = self.bv.astype(np.uint8)
+            pad = (-len(bits)) % 64
+            if pad or len(bits) == 0:
+                bits = np.concatenate([bits, np.zeros(pad if len(bits) else 64, dtype=np.uint8)])
+            self._words = np.packbits(bits, bitorder="little").view(np.uint64).copy()
+        return self._words
 
     @staticmethod
     def from_bits(bits):
         d = DensityTracker()
-        d.bv = [bool(b) for b in bits]
+        d._bits = np.array(bits, dtype=bool).reshape(-1)
+        d._n = d._bits.size
         return d
 
 

@@ -170,7 +170,8 @@ def prove_bench(w, log_m, steps, no_cpu_baseline=False, cpu_sample_log=16):
     launches = (w.launch_count() - launches0) // steps
     res = {
         "metric": "groth16_prove_seconds", "constraints": 1 << log_m, "value": min(times), "unit": "s",
-        "mean_s": sum(times) / len(times), "steps": steps, "higher_is_better": False,
+        "mean_s": sum(times) / len(times), "all_s": [round(t, 4) for t in times], "steps": steps,
+        "higher_is_better": False,
         "timed_region": "prover.rs:206-350 through bmpc_create_proof: pinned host a,b,c + assignments + "
                         "densities -> H2D -> 7 NTT + 8 MSM + tail -> 192-byte proof D2H",
         "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": 192,
