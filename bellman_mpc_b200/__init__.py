@@ -192,6 +192,11 @@ class Bases:
                                                C.byref(h)), self.worker.ctx)
         return Bases(self.worker, h)
 
+    def precompute(self, window_bits=0):
+        """window tables 2^(c w) * P_i in HBM (one bucket set, no doubling fold); returns self"""
+        _raise(self._lib.bmpc_bases_precompute(self.worker.ctx, self.handle, window_bits), self.worker.ctx)
+        return self
+
     @property
     def group(self):
         return self._lib.bmpc_bases_group(self.handle)

@@ -20,7 +20,7 @@ FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
 EXPORTS = [
     "bmpc_ctx_create", "bmpc_ctx_destroy", "bmpc_last_error", "bmpc_ctx_set_tuning",
     "bmpc_ctx_launch_count", "bmpc_ctx_profile", "bmpc_ctx_profile_read",
-    "bmpc_bases_register", "bmpc_bases_register_dev", "bmpc_bases_len", "bmpc_bases_group",
+    "bmpc_bases_register", "bmpc_bases_register_dev", "bmpc_bases_precompute", "bmpc_bases_len", "bmpc_bases_group",
     "bmpc_bases_read", "bmpc_bases_dev_ptr", "bmpc_bases_free",
     "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_sum_partials",
     "bmpc_partial_bytes",
@@ -74,6 +74,7 @@ def load():
         "bmpc_ctx_profile_read": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
         "bmpc_bases_register": (i32, [vp, i32, vp, sz, sz, i32, C.POINTER(vp)]),
         "bmpc_bases_register_dev": (i32, [vp, i32, vp, sz, C.POINTER(vp), vp]),
+        "bmpc_bases_precompute": (i32, [vp, vp, i32]),
         "bmpc_bases_len": (sz, [vp]),
         "bmpc_bases_group": (i32, [vp]),
         "bmpc_bases_read": (i32, [vp, vp, sz, sz, vp]),

@@ -43,7 +43,7 @@ int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offs
     uint32_t* d_flags = reinterpret_cast<uint32_t*>(ctx->d_stage);
     uint8_t* d_bytes = ctx->d_stage + 64;
     int mode = d_partial ? 1 : 0;
-    MsmPlan p = msm_make_plan(ctx, n, d_density != nullptr);
+    MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr);
     size_t curve_bytes = bases->group == BMPC_G1 ? GroupOps<Fp>::curve_bytes(p) : GroupOps<Fp2>::curve_bytes(p);
     rc = ws_reserve(ctx, p.sort_bytes + curve_bytes);
     if (rc) return rc;
@@ -206,6 +206,32 @@ int bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont,
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
     *out = b;
+    return BMPC_OK;
+}
+
+int bmpc_bases_precompute(bmpc_ctx* ctx, bmpc_bases* b, int window_bits) {
+    if (!ctx || !b) return BMPC_ERR_INVALID;
+    if (b->tab_W || b->n == 0) return BMPC_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    uint32_t c = window_bits > 0 ? (uint32_t)window_bits : msm_table_window(b->n);
+    if (c < 2) c = 2;
+    if (c > 22) c = 22;
+    uint32_t W = 255 / c + 1;
+    if (W > 32 || (size_t)W * b->n >= ((size_t)1 << 31)) return BMPC_OK;  // not worth it / index range: stay table-free
+    size_t pb = b->group == BMPC_G1 ? 96 : 192;
+    void* d_tab;
+    CK(cudaMalloc(&d_tab, (size_t)W * b->n * pb));
+    CK(cudaMemcpyAsync(d_tab, b->d_points, b->n * pb, cudaMemcpyDeviceToDevice, st));
+    int rc = b->group == BMPC_G1 ? GroupOps<Fp>::precompute_tables(ctx, d_tab, b->n, c, W, st)
+                                 : GroupOps<Fp2>::precompute_tables(ctx, d_tab, b->n, c, W, st);
+    if (rc) { cudaFree(d_tab); return rc; }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(b->d_points));
+    b->d_points = d_tab;
+    b->tab_c = c;
+    b->tab_W = W;
     return BMPC_OK;
 }
 

@@ -8,7 +8,7 @@ namespace bmpc {
 
 template <class F>
 size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
-    return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.g.W * p.nblk, sizeof(XYZZ<F>)) + 1024;
+    return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.g.H * p.nblk, sizeof(XYZZ<F>)) + 1024;
 }
 
 template <class F>
@@ -16,7 +16,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
                             int mode, uint8_t* d_out_bytes, void* d_out_xyzz, cudaStream_t st) {
     const MsmGeom& g = p.g;
     XYZZ<F>* partials = ws_take<XYZZ<F>>(ctx, p.max_tasks);
-    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)g.W * p.nblk);
+    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
     if (!partials || !blk_out) {
         ctx->err = "msm workspace carve failed (curve)";
         return BMPC_ERR_INVALID;
@@ -37,14 +37,14 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
         size_t smem = (size_t)p.rblock * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(128 * sizeof(XYZZ<F>))));
-        dim3 grid(p.nblk, g.W);
+        dim3 grid(p.nblk, g.H);
         LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, partials, s.toff, g.B, p.S, blk_out);
     }
     {
-        size_t smem = (size_t)g.W * sizeof(XYZZ<F>);
+        size_t smem = (size_t)(BMPC_FINAL_THREADS + g.H) * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ctx, msm_final_kernel<F>, 1, 32, smem, st, blk_out, g.W, p.nblk, g.c, mode, d_out_bytes,
-               reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        LAUNCH(ctx, msm_final_kernel<F>, 1, BMPC_FINAL_THREADS, smem, st, blk_out, g.H, p.nblk, g.c, mode,
+               d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     }
     return BMPC_OK;
 }
@@ -98,6 +98,16 @@ int GroupOps<F>::fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table
     if (n)
         LAUNCH(ctx, fixed_base_mul_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,
                reinterpret_cast<const XYZZ<F>*>(d_table), d_scalars, n, reinterpret_cast<Affine<F>*>(d_out));
+    return BMPC_OK;
+}
+
+template <class F>
+int GroupOps<F>::precompute_tables(bmpc_ctx* ctx, void* d_tables, size_t n, uint32_t c, uint32_t W,
+                                   cudaStream_t st) {
+    if (!n || W <= 1) return BMPC_OK;
+    if (W > BMPC_MAX_TABLES) return BMPC_ERR_INVALID;
+    LAUNCH(ctx, msm_precompute_kernel<F>, (uint32_t)((n + 63) / 64), 64, 0, st,
+           reinterpret_cast<Affine<F>*>(d_tables), n, c, W);
     return BMPC_OK;
 }
 

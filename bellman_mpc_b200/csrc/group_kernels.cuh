@@ -165,33 +165,87 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
 }
 
 // ------------------------------------------------------------------------ 7. final
-// blk_out[W][nblk] -> window sums -> Horner (c doublings per window, multiexp.rs:244-249).
+// blk_out[H][nblk] -> per-set sums (block tree) -> Horner over the H bucket sets (c doublings
+// per set, multiexp.rs:244-249; H == 1 with precomputed tables: no doublings at all).
 // mode 0: canonical affine, uncompressed big-endian bytes to out_bytes
 // mode 1: leave the XYZZ partial in out_xyzz (sharded MSM)
+// Launch: 1 block of FINAL_THREADS threads, dynamic smem = (FINAL_THREADS + H) * sizeof(XYZZ).
+#define BMPC_FINAL_THREADS 64
 template <class F>
-__global__ void msm_final_kernel(const XYZZ<F>* blk_out, uint32_t W, uint32_t nblk, uint32_t c,
-                                 int mode, uint8_t* out_bytes, XYZZ<F>* out_xyzz) {
+__global__ void __launch_bounds__(BMPC_FINAL_THREADS)
+msm_final_kernel(const XYZZ<F>* blk_out, uint32_t H, uint32_t nblk, uint32_t c,
+                 int mode, uint8_t* out_bytes, XYZZ<F>* out_xyzz) {
     extern __shared__ uint4 final_smem[];
-    XYZZ<F>* win = reinterpret_cast<XYZZ<F>*>(final_smem);
-    for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) {
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(final_smem);
+    XYZZ<F>* win = sm + BMPC_FINAL_THREADS;
+    for (uint32_t h = 0; h < H; h++) {
         XYZZ<F> s = XYZZ<F>::identity();
-        for (uint32_t j = 0; j < nblk; j++) {
-            XYZZ<F> v = load_struct(blk_out + (size_t)w * nblk + j);
+        for (uint32_t j = threadIdx.x; j < nblk; j += BMPC_FINAL_THREADS) {
+            XYZZ<F> v = load_struct(blk_out + (size_t)h * nblk + j);
             s.add(v);
         }
-        win[w] = s;
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        for (uint32_t st = BMPC_FINAL_THREADS >> 1; st > 0; st >>= 1) {
+            if (threadIdx.x < st) {
+                XYZZ<F> x = sm[threadIdx.x], y = sm[threadIdx.x + st];
+                x.add(y);
+                sm[threadIdx.x] = x;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) win[h] = sm[0];
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x != 0) return;
     XYZZ<F> acc = XYZZ<F>::identity();
-    for (int w = (int)W - 1; w >= 0; w--) {
-        for (uint32_t j = 0; j < c; j++) acc = acc.dbl();
-        XYZZ<F> v = win[w];
+    for (int h = (int)H - 1; h >= 0; h--) {
+        if (h != (int)H - 1)
+            for (uint32_t j = 0; j < c; j++) acc = acc.dbl();
+        XYZZ<F> v = win[h];
         acc.add(v);
     }
     if (mode == 1) { store_struct(out_xyzz, acc); return; }
     Affine<F> a = acc.to_affine();
     encode_uncompressed<F>(a, out_bytes);
+}
+
+// Precomputed window tables: tables[w][i] = 2^(c w) * P_i in affine form, w = 1 .. W-1 (table 0
+// = the bases themselves).  One thread per base: chain of c doublings per table kept in XYZZ,
+// then ONE inversion per base for all tables (Montgomery's trick over the W-1 denominators).
+#define BMPC_MAX_TABLES 32
+template <class F>
+__global__ void __launch_bounds__(64)
+msm_precompute_kernel(Affine<F>* tables, size_t n, uint32_t c, uint32_t W) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = load_struct(tables + i);
+    if (p.is_identity()) {
+        for (uint32_t w = 1; w < W; w++) store_struct(tables + (size_t)w * n + i, p);
+        return;
+    }
+    XYZZ<F> pts[BMPC_MAX_TABLES];
+    F pre[BMPC_MAX_TABLES];
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    F prod = F::one();
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t j = 0; j < c; j++) acc = acc.dbl();
+        pts[w] = acc;
+        pre[w] = prod;                                  // product of the denominators before w
+        if (!acc.is_identity()) prod = F::mul_cold(prod, F::mul_cold(acc.ZZ, acc.ZZZ));
+    }
+    F inv = prod.inv();
+    for (uint32_t w = W - 1; w >= 1; w--) {
+        Affine<F> out = Affine<F>::identity();
+        if (!pts[w].is_identity()) {
+            F d = F::mul_cold(pts[w].ZZ, pts[w].ZZZ);
+            F di = F::mul_cold(inv, pre[w]);            // 1 / (ZZ * ZZZ) of table w
+            inv = F::mul_cold(inv, d);
+            out.x = F::mul_cold(pts[w].X, F::mul_cold(di, pts[w].ZZZ));
+            out.y = F::mul_cold(pts[w].Y, F::mul_cold(di, pts[w].ZZ));
+        }
+        store_struct(tables + (size_t)w * n + i, out);
+    }
 }
 
 // sum of `count` XYZZ partials (one per rank) -> canonical affine bytes

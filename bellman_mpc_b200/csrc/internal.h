@@ -62,8 +62,10 @@ struct bmpc_ctx {
 struct bmpc_bases {
     int group = 0;
     size_t n = 0;
-    void* d_points = nullptr;   // Affine<Fp>[n] or Affine<Fp2>[n], Montgomery
+    void* d_points = nullptr;   // Affine<Fp>[n] or Affine<Fp2>[n], Montgomery; with precomputed
+                                // window tables: [tab_W][n], table w holding 2^(tab_c w) * P_i
     uint32_t* d_inf = nullptr;  // identity bitmap
+    uint32_t tab_c = 0, tab_W = 0;  // 0 = no tables
 };
 
 struct bmpc_domain {
@@ -172,6 +174,8 @@ struct MsmGeom {
     uint32_t W;        // number of windows = 255 / c + 1
     uint32_t B;        // buckets per window = 2^(c-1)  (signed digits)
     uint32_t L;        // max points per accumulate task
+    uint32_t H;        // bucket sets: W without precomputed tables, 1 with them
+    uint32_t tab_stride; // entries per precomputed table (0 without tables)
     uint32_t c_ref;    // the reference's window size for this n (error precedence only)
     uint32_t top_skip; // bit offset of the reference's highest window
 };
@@ -192,7 +196,8 @@ struct MsmSorted {      // outputs of the sort stage (device pointers into the a
     uint32_t* heavy_count;
 };
 
-MsmPlan msm_make_plan(bmpc_ctx* ctx, size_t n, bool has_density);
+MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density);
+uint32_t msm_table_window(size_t n_bases);  // window bits used for precomputed tables
 // count -> scan -> scatter; raises EOF / identity flags into d_flags[0]
 int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,
                  const uint32_t* d_scalars, size_t n, const uint32_t* d_density, uint32_t* d_flags,
@@ -216,6 +221,9 @@ struct GroupOps {
                          size_t n, void* d_out, cudaStream_t st);
     static int fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table, const uint32_t* d_scalars,
                               size_t n, void* d_out, cudaStream_t st);
+    // d_tables: [W][n] with table 0 already filled; fills tables 1..W-1 (2^(c w) * P_i, affine)
+    static int precompute_tables(bmpc_ctx* ctx, void* d_tables, size_t n, uint32_t c, uint32_t W,
+                                 cudaStream_t st);
 };
 
 // ---------------------------------------------------------------- prove.cu

@@ -16,11 +16,24 @@ static inline size_t scan_chunks_words(uint32_t n) {
     return (n + BMPC_SCAN_CHUNK - 1) / BMPC_SCAN_CHUNK + 2;
 }
 
-MsmPlan msm_make_plan(bmpc_ctx* ctx, size_t n, bool has_density) {
+// Window bits for precomputed tables: all windows share one bucket set, so the bucket count can
+// grow until the (parallel) bucket reduction matters: 2^(c-1) ~ n / 8.
+uint32_t msm_table_window(size_t n_bases) {
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n_bases) lg++;
+    uint32_t c = lg > 6 ? lg - 2 : 4;
+    if (c > 22) c = 22;
+    if (c < 4) c = 4;
+    return c;
+}
+
+MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density) {
     MsmPlan p;
     MsmGeom& g = p.g;
     uint32_t c;
-    if (ctx->tune_c) c = (uint32_t)ctx->tune_c;
+    bool tables = bases->tab_W != 0;
+    if (tables) c = bases->tab_c;
+    else if (ctx->tune_c) c = (uint32_t)ctx->tune_c;
     else {
         uint32_t lg = 0;
         while (((size_t)1 << (lg + 1)) <= n) lg++;
@@ -28,18 +41,22 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, size_t n, bool has_density) {
         if (c > 16) c = 16;
     }
     if (c < 2) c = 2;
-    if (c > 20) c = 20;
+    if (c > 22) c = 22;
     g.c = c;
     g.W = 255 / c + 1;
     g.B = 1u << (c - 1);
-    size_t avg = n / g.B;
+    g.H = tables ? 1u : g.W;
+    g.tab_stride = tables ? (uint32_t)bases->n : 0u;
+    size_t avg = n * (g.W / g.H) / g.B;
     g.L = (uint32_t)(2 * avg < 64 ? 64 : 2 * avg);
     g.c_ref = reference_window(n);
     g.top_skip = (254 / g.c_ref) * g.c_ref;
-    p.nb = g.W * g.B;
+    p.nb = g.H * g.B;
     p.max_pairs = n * g.W;
     p.max_tasks = p.max_pairs / g.L + p.nb + 1;
-    p.tpw = g.B < 1024 ? g.B : 1024;
+    // reduce: each thread owns S consecutive buckets of one set (S >= 1), blocks of <= 128 threads
+    uint32_t max_tpw = g.H == 1 ? 65536u : 1024u;
+    p.tpw = g.B < max_tpw ? g.B : max_tpw;
     p.rblock = p.tpw < 128 ? p.tpw : 128;
     p.S = g.B / p.tpw;
     p.nblk = p.tpw / p.rblock;

@@ -75,6 +75,8 @@ __device__ __forceinline__ bool for_each_digit(const MsmInput& in, const MsmGeom
         uint32_t d = get_bits(s, w * g.c, g.c) + carry;
         bool neg = d > half;
         if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
+        // window w -> bucket set (w % H), table (w / H): with precomputed tables H == 1 and
+        // every window adds table_w[i] = 2^(c w) P_i into the same bucket set
         if (d != 0) f(w, d - 1u, neg);
     }
     return true;
@@ -85,7 +87,7 @@ __global__ void msm_count_kernel(MsmInput in, MsmGeom g, uint32_t* hist, uint32_
     if (i >= in.n) return;
     uint32_t base_idx;
     for_each_digit(in, g, i, flags, true, base_idx,
-                   [&](uint32_t w, uint32_t b, bool) { atomicAdd(hist + (size_t)w * g.B + b, 1u); });
+                   [&](uint32_t w, uint32_t b, bool) { atomicAdd(hist + (size_t)(w % g.H) * g.B + b, 1u); });
 }
 
 __global__ void msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uint32_t* sorted) {
@@ -93,8 +95,8 @@ __global__ void msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uin
     if (i >= in.n) return;
     uint32_t base_idx;
     for_each_digit(in, g, i, nullptr, false, base_idx, [&](uint32_t w, uint32_t b, bool neg) {
-        uint32_t pos = atomicAdd(cursor + (size_t)w * g.B + b, 1u);
-        sorted[pos] = base_idx | (neg ? 0x80000000u : 0u);
+        uint32_t pos = atomicAdd(cursor + (size_t)(w % g.H) * g.B + b, 1u);
+        sorted[pos] = (base_idx + (w / g.H) * g.tab_stride) | (neg ? 0x80000000u : 0u);
     });
 }
 

@@ -181,6 +181,8 @@ def run_ours(args):
     ks = rand_limbs(n, 2 + 7919 * rank)
     t_setup = time.perf_counter()
     bases = bm.Bases.fixed_base_mul(w, bm.G1, curves_gen, ks)          # resident CRS slice, k_i * G
+    if not args.no_precompute:
+        bases.precompute()                                               # window tables in HBM (setup)
     scalars_h = torch.from_numpy(rand_limbs(n, 1 + 7919 * rank).view(np.int64)).pin_memory()
     scalars_d = scalars_h.to(dev)
     torch.cuda.synchronize()
@@ -289,7 +291,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u32-limb Montgomery (Fp 12x32, Fr 8x32)", "data": "synthetic",
         "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity "
                                f"(BASELINE configs[1] shape at the size the metric is quoted on)",
-                   "bases": "k_i*G, resident (CRS registered once)", "points_per_gpu": n,
+                   "bases": "k_i*G, resident (CRS registered once%s)" % ("" if args.no_precompute else
+                            ", window tables 2^(cw)*P_i precomputed at registration"), "points_per_gpu": n,
                    "l2": "inputs larger than L2 (scalars %d MiB + bases %d MiB per GPU)" % (n * 32 >> 20, n * 96 >> 20),
                    "parallelism": f"bases split x{world}, all-gather of {pbytes}-byte partials" if world > 1 else "single GPU",
                    "setup_s": round(t_setup, 2)},
@@ -322,7 +325,8 @@ def run_ours(args):
     if world == 1 and not args.no_prove:
         try:
             from bench_prove import prove_bench
-            line["prove"] = prove_bench(w, args.prove_log_n, max(2, args.steps // 2), args.no_cpu_baseline)
+            line["prove"] = prove_bench(w, args.prove_log_n, max(2, args.steps // 2), args.no_cpu_baseline,
+                                        precompute=not args.no_precompute)
         except Exception as e:  # keep the headline line even if the secondary workload fails
             line["prove"] = {"error": repr(e)}
 
@@ -345,6 +349,7 @@ def main():
     ap.add_argument("--prove-log-n", type=int, default=22)
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-precompute", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

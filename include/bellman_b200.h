@@ -87,6 +87,11 @@ int  bmpc_bases_register(bmpc_ctx* ctx, int group, const void* points, size_t n,
 /* same, from a device array of Montgomery x|y points (copied) */
 int  bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont, size_t n,
                              bmpc_bases** out, void* stream);
+/* Precompute window tables 2^(c w) * P_i for w = 1 .. W-1 next to the bases (W x the memory, laid
+ * out for the 180 GB of HBM): every window of a later multiexp then feeds ONE bucket set and the
+ * top-down doubling fold of multiexp.rs:244-249 disappears.  window_bits = 0 picks c from n.
+ * Results are unchanged (window-independent, SURVEY 8a'/7); call once per CRS vector. */
+int  bmpc_bases_precompute(bmpc_ctx* ctx, bmpc_bases* b, int window_bits);
 size_t bmpc_bases_len(const bmpc_bases* b);
 int  bmpc_bases_group(const bmpc_bases* b);
 /* read points [start, start+count) back as uncompressed big-endian (tests / CRS export) */

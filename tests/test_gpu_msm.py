@@ -179,6 +179,39 @@ def test_error_semantics(worker):
     assert _error_case(worker, p1, 0, None, s6) == "identity"
 
 
+@pytest.mark.parametrize("group,n,c", [(bm.G1, 5000, 0), (bm.G1, 3000, 9), (bm.G2, 1500, 0), (bm.G1, 1 << 16, 0)])
+def test_precomputed_tables(worker, group, n, c):
+    """window tables 2^(cw) P_i (one bucket set, no doubling fold) give the same bytes, also with
+    density maps, offsets and the error semantics"""
+    ks = rand_scalars(n + 7, 50)
+    scalars = rand_scalars(n, 51, "mixed")
+    bases = known_dlog_bases(worker, group, ks).precompute(c)
+    assert _run(worker, bases, 0, bm.FullDensity(), scalars) == expected_from_dlogs(group, ks, scalars)
+    rng = random.Random(52)
+    bits = [rng.random() < 0.5 for _ in range(n)]
+    got = _run(worker, bases, 5, bm.DensityTracker.from_bits(bits), scalars)
+    assert got == expected_from_dlogs(group, ks, scalars, bits, 5)
+    with pytest.raises(bm.UnexpectedEof):
+        _run(worker, bases, 8, bm.FullDensity(), scalars)
+    assert bases.read(0, 3) == known_dlog_bases(worker, group, ks[:3]).read()
+    bases.free()
+
+
+def test_precomputed_identity_base(worker):
+    G = curves.G1
+    rng = random.Random(53)
+    n = 600
+    pts = [G.mul(G.gen, rng.randrange(1, Q)) for _ in range(n)]
+    pts[17] = None
+    sc = [rng.randrange(Q) for _ in range(n)]
+    bases = bm.Bases.from_uncompressed(worker, bm.G1, b"".join(G.to_uncompressed(p) for p in pts)).precompute(8)
+    with pytest.raises(bm.UnexpectedIdentity):
+        _run(worker, bases, 0, bm.FullDensity(), sc)
+    sc[17] = 0
+    assert decode(bm.G1, _run(worker, bases, 0, bm.FullDensity(), sc)) == ome.naive(G, pts[:17] + pts[18:], sc[:17] + sc[18:])
+    bases.free()
+
+
 def test_batch_scalar_mul(worker):
     """mpc.rs:647-706: per-element and same-scalar batch multiplication, G1 and G2"""
     for group in (bm.G1, bm.G2):
