@@ -105,8 +105,11 @@ void bmpc_ctx_destroy(bmpc_ctx* ctx) {
     cudaDeviceSynchronize();
     ntt_free_tables(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->io) cudaFree(ctx->io);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -272,6 +275,16 @@ void bmpc_bases_free(bmpc_ctx* ctx, bmpc_bases* b) {
 // ------------------------------------------------------------------------- multiexp
 size_t bmpc_partial_bytes(int group) { return group == BMPC_G1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ); }
 
+int bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t* window_bits,
+                      uint32_t* windows, uint32_t* bucket_sets) {
+    if (!ctx || !bases) return BMPC_ERR_INVALID;
+    MsmPlan p = msm_make_plan(ctx, bases, n, false);
+    if (window_bits) *window_bits = p.g.c;
+    if (windows) *windows = p.g.W;
+    if (bucket_sets) *bucket_sets = p.g.H;
+    return BMPC_OK;
+}
+
 int bmpc_multiexp_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
                       const uint64_t* d_scalars, size_t n, const uint64_t* d_density_words,
                       size_t density_len, uint8_t* out, void* stream) {
@@ -303,18 +316,17 @@ int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, co
     uint64_t* d_d = nullptr;
     size_t dw = (n + 63) / 64;
     if (n) {
-        CK(cudaMalloc(&d_s, n * 32));
+        size_t sbytes = align_up(n * 32, 256);
+        int rr = io_reserve(ctx, sbytes + dw * 8 + 256);
+        if (rr) return rr;
+        d_s = reinterpret_cast<uint64_t*>(ctx->io);
         CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
         if (density_words) {
-            CK(cudaMalloc(&d_d, dw * 8));
+            d_d = reinterpret_cast<uint64_t*>(ctx->io + sbytes);
             CK(cudaMemcpyAsync(d_d, density_words, dw * 8, cudaMemcpyHostToDevice, st));
         }
     }
-    int rc = multiexp_dev_locked(ctx, bases, base_offset, d_s, n, d_d, density_len, out, nullptr, st);
-    cudaStreamSynchronize(st);
-    if (d_s) cudaFree(d_s);
-    if (d_d) cudaFree(d_d);
-    return rc;
+    return multiexp_dev_locked(ctx, bases, base_offset, d_s, n, d_d, density_len, out, nullptr, st);
 }
 
 int bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count, uint8_t* out,
@@ -565,14 +577,36 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
         exp++;
         if (exp >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;  // from_coeffs, prover.rs:211
     }
-    // persistent buffers for this proof (outside the per-MSM scratch arena)
-    Fr *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_in = nullptr, *d_aux = nullptr;
-    uint64_t *d_da = nullptr, *d_dbi = nullptr, *d_dba = nullptr;
-    uint8_t* d_misc = nullptr;  // partials + vk + r,s + proof
+    // Device buffers for this proof come out of the grow-only staging area (no cudaMalloc/cudaFree
+    // per proof).  The big a, b, c upload runs on a second stream and overlaps the seven
+    // multiexps that only need the assignments; the H pipeline waits for it.
+    const size_t dwi = (ni + 63) / 64, dwa = (na + 63) / 64;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1, 256); return o; };
+    const size_t o_a = carve(m * 32), o_b = carve(m * 32), o_c = carve(m * 32);
+    const size_t o_in = carve(ni * 32), o_aux = carve(na * 32);
+    const size_t o_da = carve(dwa * 8), o_dbi = carve(dwi * 8), o_dba = carve(dwa * 8), o_misc = carve(8192);
+    {
+        int rr = io_reserve(ctx, off);
+        if (rr) return rr;
+    }
+    Fr* d_a = reinterpret_cast<Fr*>(ctx->io + o_a);
+    Fr* d_b = reinterpret_cast<Fr*>(ctx->io + o_b);
+    Fr* d_c = reinterpret_cast<Fr*>(ctx->io + o_c);
+    Fr* d_in = reinterpret_cast<Fr*>(ctx->io + o_in);
+    Fr* d_aux = reinterpret_cast<Fr*>(ctx->io + o_aux);
+    uint64_t* d_da = reinterpret_cast<uint64_t*>(ctx->io + o_da);
+    uint64_t* d_dbi = reinterpret_cast<uint64_t*>(ctx->io + o_dbi);
+    uint64_t* d_dba = reinterpret_cast<uint64_t*>(ctx->io + o_dba);
+    uint8_t* d_misc = reinterpret_cast<uint8_t*>(ctx->io + o_misc);  // partials + vk + r,s + proof
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = ctx->copy_stream;
     auto cleanup = [&]() {
+        cudaStreamSynchronize(cs);
         cudaStreamSynchronize(st);
-        cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); cudaFree(d_in); cudaFree(d_aux);
-        cudaFree(d_da); cudaFree(d_dbi); cudaFree(d_dba); cudaFree(d_misc);
     };
 #define CKP(call)                                                            \
     do {                                                                     \
@@ -591,23 +625,20 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
             return rc_;            \
         }                          \
     } while (0)
-    CKP(cudaMalloc(&d_a, m * 32)); CKP(cudaMalloc(&d_b, m * 32)); CKP(cudaMalloc(&d_c, m * 32));
-    CKP(cudaMalloc(&d_in, (ni ? ni : 1) * 32)); CKP(cudaMalloc(&d_aux, (na ? na : 1) * 32));
-    size_t dwi = (ni + 63) / 64, dwa = (na + 63) / 64;
-    CKP(cudaMalloc(&d_da, (dwa ? dwa : 1) * 8)); CKP(cudaMalloc(&d_dbi, (dwi ? dwi : 1) * 8));
-    CKP(cudaMalloc(&d_dba, (dwa ? dwa : 1) * 8));
-    CKP(cudaMalloc(&d_misc, 8192));
-    const Fr* srcs[3] = {(const Fr*)S->a, (const Fr*)S->b, (const Fr*)S->c};
-    Fr* dsts[3] = {d_a, d_b, d_c};
-    for (int k = 0; k < 3; k++) {
-        if (nc) CKP(cudaMemcpyAsync(dsts[k], srcs[k], nc * 32, cudaMemcpyHostToDevice, st));
-        if (m > nc) CKP(cudaMemsetAsync(dsts[k] + nc, 0, (m - nc) * 32, st));
-    }
+    // small inputs first, on the compute stream
     if (ni) CKP(cudaMemcpyAsync(d_in, S->input_assignment, ni * 32, cudaMemcpyHostToDevice, st));
     if (na) CKP(cudaMemcpyAsync(d_aux, S->aux_assignment, na * 32, cudaMemcpyHostToDevice, st));
     if (dwa) CKP(cudaMemcpyAsync(d_da, S->a_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
     if (dwi) CKP(cudaMemcpyAsync(d_dbi, S->b_input_density, dwi * 8, cudaMemcpyHostToDevice, st));
     if (dwa) CKP(cudaMemcpyAsync(d_dba, S->b_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
+    // evaluation vectors on the copy stream
+    const Fr* srcs[3] = {(const Fr*)S->a, (const Fr*)S->b, (const Fr*)S->c};
+    Fr* dsts[3] = {d_a, d_b, d_c};
+    for (int k = 0; k < 3; k++) {
+        if (nc) CKP(cudaMemcpyAsync(dsts[k], srcs[k], nc * 32, cudaMemcpyHostToDevice, cs));
+        if (m > nc) CKP(cudaMemsetAsync(dsts[k] + nc, 0, (m - nc) * 32, cs));
+    }
+    CKP(cudaEventRecord(ctx->copy_done, cs));
 
     // layout of d_misc
     G1XYZZ* part_g1 = reinterpret_cast<G1XYZZ*>(d_misc);              // 6 x 192
@@ -626,13 +657,6 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
     RCP(GroupOps<Fp>::decode(ctx, d_vkraw, 96, 3, vk_g1, st));
     RCP(GroupOps<Fp2>::decode(ctx, d_vkraw + 288, 192, 2, vk_g2, st));
 
-    // H polynomial (prover.rs:210-231)
-    {
-        RCP(ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr))));
-        Fr* t1 = ws_take<Fr>(ctx, m);
-        Fr* t2 = ws_take<Fr>(ctx, m);
-        RCP(h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, st));
-    }
     // to_le_bits of the assignments (prover.rs:237-250)
     RCP(fr_pointwise(ctx, 2, d_in, nullptr, ni, st));
     RCP(fr_pointwise(ctx, 2, d_aux, nullptr, na, st));
@@ -652,7 +676,17 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
         {P->l, 0, (uint64_t*)d_aux, na, nullptr, part_g1 + 5},           // l          :252-257
     };
     int statuses[8];
-    for (int j = 0; j < 8; j++) {
+    const int order[8] = {0, 1, 2, 3, 4, 5, 7, 6};  // H last: it needs the uploaded a, b, c
+    for (int k = 0; k < 8; k++) {
+        int j = order[k];
+        if (j == 6) {
+            // H polynomial (prover.rs:210-231)
+            CKP(cudaStreamWaitEvent(st, ctx->copy_done, 0));
+            RCP(ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr))));
+            Fr* t1 = ws_take<Fr>(ctx, m);
+            Fr* t2 = ws_take<Fr>(ctx, m);
+            RCP(h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, st));
+        }
         int rc = multiexp_dev_locked(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens,
                                      jobs[j].n, nullptr, jobs[j].out, st);
         if (rc == BMPC_ERR_CUDA || rc == BMPC_ERR_INVALID || rc == BMPC_ERR_LENGTH_MISMATCH) {

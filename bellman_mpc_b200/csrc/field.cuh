@@ -261,7 +261,86 @@ struct Field {
         final_sub(r.l, even);
         return r;
     }
-    BMPC_HD Field sqr() const { return *this * *this; }
+    // Montgomery square a * a * R^-1 mod p: N(N-1)/2 off-diagonal products (doubled) + N
+    // diagonal ones, then a word-by-word REDC -- (N^2+N)/2 + N^2 + N MAC32 instead of 2N^2 + N
+    // (234 vs 300 for Fp).
+    BMPC_HD Field sqr() const {
+        constexpr int N2 = 2 * N;
+        const uint32_t* a = l;
+        uint32_t d[N2];
+#pragma unroll
+        for (int k = 0; k < N2; k++) d[k] = 0;
+        // Row i adds a_i * a_j (j > i) at limb i + j.  Products whose offset k = j - i has the
+        // same parity tile contiguous limb pairs, so each parity class is one carry chain.  The
+        // class NOT holding the last term ends one limb lower and runs first: its carry-out then
+        // lands on a limb that so far only holds a carry bit, and the second chain's carry-out on
+        // an untouched limb (rows grow the top by one limb each), so no ripple is ever needed.
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            const int K = N - 1 - i;
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                const int ks = (pass == 0) ? ((K & 1) ? 2 : 1) : ((K & 1) ? 1 : 2);
+                if (ks <= K) {
+                    int last = 0;
+#pragma unroll
+                    for (int k = ks; k <= K; k += 2) {
+                        const int j = i + k, pos = i + j;
+                        if (k == ks) d[pos] = mad_lo_cc(a[i], a[j], d[pos]);
+                        else d[pos] = madc_lo_cc(a[i], a[j], d[pos]);
+                        d[pos + 1] = madc_hi_cc(a[i], a[j], d[pos + 1]);
+                        last = pos + 1;
+                    }
+                    d[last + 1] = addc(d[last + 1], 0);
+                }
+            }
+        }
+        // t = 2 d + sum a_i^2 2^(64 i)
+        uint32_t t[N2];
+#pragma unroll
+        for (int k = N2 - 1; k >= 1; k--) t[k] = (d[k] << 1) | (d[k - 1] >> 31);
+        t[0] = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i == 0) t[0] = mad_lo_cc(a[0], a[0], t[0]);
+            else t[2 * i] = madc_lo_cc(a[i], a[i], t[2 * i]);
+            t[2 * i + 1] = madc_hi_cc(a[i], a[i], t[2 * i + 1]);
+        }
+        // REDC: for each low limb add m p so it vanishes.  The two carry-outs of row i land on
+        // limbs i+N and i+N+1; they are counted separately and folded in once at the end, so
+        // the rows need no ripple either.
+        uint32_t cy[N + 1];
+#pragma unroll
+        for (int k = 0; k <= N; k++) cy[k] = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t m = t[i] * P::INV;
+            t[i] = mad_lo_cc(m, P::mod(0), t[i]);
+            t[i + 1] = madc_hi_cc(m, P::mod(0), t[i + 1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                t[i + j] = madc_lo_cc(m, P::mod(j), t[i + j]);
+                t[i + j + 1] = madc_hi_cc(m, P::mod(j), t[i + j + 1]);
+            }
+            cy[i] = addc(cy[i], 0);
+            t[i + 1] = mad_lo_cc(m, P::mod(1), t[i + 1]);
+            t[i + 2] = madc_hi_cc(m, P::mod(1), t[i + 2]);
+#pragma unroll
+            for (int j = 3; j < N; j += 2) {
+                t[i + j] = madc_lo_cc(m, P::mod(j), t[i + j]);
+                t[i + j + 1] = madc_hi_cc(m, P::mod(j), t[i + j + 1]);
+            }
+            cy[i + 1] = addc(cy[i + 1], 0);
+        }
+        uint32_t r[N];
+        r[0] = add_cc(t[N], cy[0]);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) r[k] = addc_cc(t[N + k], cy[k]);
+        r[N - 1] = addc(t[2 * N - 1], cy[N - 1]);
+        Field out;
+        final_sub(out.l, r);
+        return out;
+    }
     // out-of-line product for cold paths
     BMPC_COLD static Field mul_cold(const Field& a, const Field& b) { return a * b; }
 

@@ -25,7 +25,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
     {
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
-        LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.off, s.toff, p.nb, g.L, partials);
+        LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.desc, s.ntasks, partials);
     }
     ProfScope ps_tail(ctx, BMPC_PROF_MSM_REDUCE, st);
     {

@@ -57,26 +57,17 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
     return r;
 }
 // --------------------------------------------------------------------- 4. accumulate
-// off[nb+1]: bucket offsets into `sorted`; toff[nb+1]: task offsets.  Task t belongs to the
-// bucket b with toff[b] <= t < toff[b+1] and covers sorted[off[b] + k L, ...) for k = t - toff[b].
+// One thread per task; a task is a slice of <= L consecutive entries of one bucket in `sorted`,
+// described by desc[t] (built by task_desc_kernel, big tasks first so warps stay balanced).
 template <class F>
 __global__ void __launch_bounds__(128)
-msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint32_t* off,
-                      const uint32_t* toff, uint32_t nb, uint32_t L, XYZZ<F>* partials) {
-    uint32_t ntasks = toff[nb];
+msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint4* desc,
+                      const uint32_t* ntasks_p, XYZZ<F>* partials) {
+    uint32_t ntasks = *ntasks_p;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntasks) return;
-    // largest b with toff[b] <= t
-    uint32_t lo = 0, hi = nb;  // invariant: toff[lo] <= t, answer in [lo, hi)
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(toff + mid) <= t) lo = mid; else hi = mid;
-    }
-    uint32_t b = lo;
-    uint32_t k = t - __ldg(toff + b);
-    uint32_t start = __ldg(off + b) + k * L;
-    uint32_t end = __ldg(off + b + 1);
-    if (end > start + L) end = start + L;
+    uint4 d = __ldg(desc + t);     // {first entry, length, partial slot, bucket}; big tasks first
+    uint32_t start = d.x, end = d.x + d.y;
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t j = start; j < end; j++) {
         uint32_t e = __ldg(sorted + j);
@@ -84,7 +75,7 @@ msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint
         if (e & 0x80000000u) p.y = p.y.neg();
         acc.add_affine(p);
     }
-    store_struct(partials + t, acc);
+    store_struct(partials + d.z, acc);
 }
 
 // ------------------------------------------------------------------ 5. heavy buckets

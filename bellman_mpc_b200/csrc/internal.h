@@ -43,9 +43,15 @@ struct bmpc_ctx {
     uint64_t launches = 0;
     int tune_c = 0, tune_maxdeg = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // H2D of large inputs overlapping compute (create_proof)
+    cudaEvent_t copy_done = nullptr;
     // scratch arena (grown on demand, reused across calls)
     char* ws = nullptr;
     size_t ws_size = 0, ws_used = 0;
+    // device staging for host-pointer entry points (scalars, density words); grow-only so that a
+    // prover calling in a loop does not pay cudaMalloc/cudaFree per call
+    char* io = nullptr;
+    size_t io_size = 0;
     // staging for small results
     uint8_t* h_stage = nullptr;  // 4 KB pinned
     uint8_t* d_stage = nullptr;  // 4 KB
@@ -144,6 +150,17 @@ inline int ws_reserve(bmpc_ctx* ctx, size_t bytes) {
     ctx->ws_size = want;
     return BMPC_OK;
 }
+inline int io_reserve(bmpc_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->io_size) return BMPC_OK;
+    CK(cudaDeviceSynchronize());
+    if (ctx->io) CK(cudaFree(ctx->io));
+    ctx->io = nullptr;
+    ctx->io_size = 0;
+    size_t want = align_up(bytes, 1 << 20);
+    CK(cudaMalloc(&ctx->io, want));
+    ctx->io_size = want;
+    return BMPC_OK;
+}
 template <class T>
 inline T* ws_take(bmpc_ctx* ctx, size_t count) {
     size_t bytes = align_up(count * sizeof(T), 256);
@@ -194,6 +211,8 @@ struct MsmSorted {      // outputs of the sort stage (device pointers into the a
     uint32_t* toff;     // nb + 1 task offsets
     uint32_t* heavy;    // nb + 1 scratch for the heavy-bucket list
     uint32_t* heavy_count;
+    uint4* desc;        // per task {first sorted entry, length, partial slot, bucket}, big tasks first
+    uint32_t* ntasks;   // device pointer to the task count (== toff[nb])
 };
 
 MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density);

@@ -66,7 +66,8 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     b += ws_need(p.nb + 1, 4) * 5;  // hist, off, toff, cursor, heavy
     b += ws_need(scan_chunks_words(p.nb), 4);
     b += ws_need(p.max_pairs + 1, 4);  // sorted
-    b += ws_need(64, 4);
+    b += ws_need(64, 4) + ws_need(256, 4);
+    b += ws_need(p.max_tasks, 16);     // task descriptors
     p.sort_bytes = b + 4096;
     return p;
 }
@@ -118,6 +119,12 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     uint32_t* chunks = ws_take<uint32_t>(ctx, scan_chunks_words(p.nb));
     uint32_t* sorted = ws_take<uint32_t>(ctx, p.max_pairs + 1);
     uint32_t* heavy_count = ws_take<uint32_t>(ctx, 64);
+    uint32_t* bins = ws_take<uint32_t>(ctx, 256);
+    uint4* desc = ws_take<uint4>(ctx, p.max_tasks);
+    if (!bins || !desc) {
+        ctx->err = "msm workspace carve failed (tasks)";
+        return BMPC_ERR_INVALID;
+    }
     if (!hist || !off || !toff || !cursor || !heavy || !chunks || !sorted || !heavy_count) {
         ctx->err = "msm workspace carve failed";
         return BMPC_ERR_INVALID;
@@ -133,6 +140,12 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     CK(cudaMemcpyAsync(cursor, off, (size_t)p.nb * 4, cudaMemcpyDeviceToDevice, st));
     LAUNCH(ctx, msm_scatter_kernel, nblocks, 256, 0, st, in, g, cursor, sorted);
     LAUNCH(ctx, msm_find_heavy_kernel, (p.nb + 255) / 256, 256, 0, st, toff, p.nb, heavy, heavy_count);
+    CK(cudaMemsetAsync(bins, 0, 256 * 4, st));
+    LAUNCH(ctx, task_bin_count_kernel, (p.nb + 255) / 256, 256, 0, st, off, toff, p.nb, g.L, bins);
+    LAUNCH(ctx, task_bin_scan_kernel, 1, 1, 0, st, bins);
+    LAUNCH(ctx, task_desc_kernel, (p.nb + 255) / 256, 256, 0, st, off, toff, p.nb, g.L, bins, desc);
+    out->desc = desc;
+    out->ntasks = toff + p.nb;
     out->sorted = sorted;
     out->off = off;
     out->toff = toff;

@@ -90,14 +90,47 @@ __global__ void msm_count_kernel(MsmInput in, MsmGeom g, uint32_t* hist, uint32_
                    [&](uint32_t w, uint32_t b, bool) { atomicAdd(hist + (size_t)(w % g.H) * g.B + b, 1u); });
 }
 
+// Scatter: the slot of each (position, window) pair comes back from an atomicAdd; the returning
+// atomics of GROUP windows are issued back to back so their L2 round trips overlap, then the
+// GROUP stores go out.
 __global__ void msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uint32_t* sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= in.n) return;
     uint32_t base_idx;
-    for_each_digit(in, g, i, nullptr, false, base_idx, [&](uint32_t w, uint32_t b, bool neg) {
-        uint32_t pos = atomicAdd(cursor + (size_t)(w % g.H) * g.B + b, 1u);
-        sorted[pos] = (base_idx + (w / g.H) * g.tab_stride) | (neg ? 0x80000000u : 0u);
-    });
+    if (!resolve_base(in, i, base_idx)) return;
+    if (base_idx >= in.bases_len) return;
+    uint32_t s[8];
+    load_scalar(in.scalars + i * 8, s);
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+    if ((__ldg(in.inf_bitmap + (base_idx >> 5)) >> (base_idx & 31)) & 1u) return;
+    constexpr int GROUP = 4;
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (g.c - 1);
+    for (uint32_t w0 = 0; w0 < g.W; w0 += GROUP) {
+        uint32_t key[GROUP], val[GROUP], pos[GROUP];
+        bool live[GROUP];
+#pragma unroll
+        for (int j = 0; j < GROUP; j++) {
+            uint32_t w = w0 + j;
+            live[j] = false;
+            if (w < g.W) {
+                uint32_t d = get_bits(s, w * g.c, g.c) + carry;
+                bool neg = d > half;
+                if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
+                if (d != 0) {
+                    live[j] = true;
+                    key[j] = (w % g.H) * g.B + (d - 1u);
+                    val[j] = (base_idx + (w / g.H) * g.tab_stride) | (neg ? 0x80000000u : 0u);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GROUP; j++)
+            if (live[j]) pos[j] = atomicAdd(cursor + key[j], 1u);
+#pragma unroll
+        for (int j = 0; j < GROUP; j++)
+            if (live[j]) sorted[pos[j]] = val[j];
+    }
 }
 
 // ---------------------------------------------------------------- density prefix popcount
@@ -192,6 +225,70 @@ scan_phase3_kernel(const uint32_t* in, uint32_t n, uint32_t L, const uint32_t* c
         ex += v[j];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = chunk_sums[nchunks];
+}
+
+// ------------------------------------------------------------- task ordering by size
+// Threads of a warp run until the longest of their 32 tasks finishes, so tasks are handed out
+// in (approximately) descending size order: a 64-bin counting sort of the task lengths.  Each
+// task gets a descriptor {first sorted entry, length, partial-sum slot}.
+#define BMPC_TASK_BINS 64
+__device__ __forceinline__ uint32_t task_bin(uint32_t len, uint32_t L) {
+    return (BMPC_TASK_BINS - 1u) - (len * (BMPC_TASK_BINS - 1u)) / L;   // big tasks -> low bins
+}
+__global__ void __launch_bounds__(256)
+task_bin_count_kernel(const uint32_t* off, const uint32_t* toff, uint32_t nb, uint32_t L, uint32_t* bin_hist) {
+    __shared__ uint32_t sh[BMPC_TASK_BINS];
+    if (threadIdx.x < BMPC_TASK_BINS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) {
+        uint32_t cnt = off[b + 1] - off[b];
+        uint32_t nt = toff[b + 1] - toff[b];
+        if (nt > 1) atomicAdd(&sh[task_bin(L, L)], nt - 1u);
+        if (nt > 0) atomicAdd(&sh[task_bin(cnt - (nt - 1u) * L, L)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < BMPC_TASK_BINS && sh[threadIdx.x]) atomicAdd(bin_hist + threadIdx.x, sh[threadIdx.x]);
+}
+// bin_hist[BINS] -> exclusive starts in place (single thread; 64 entries)
+__global__ void task_bin_scan_kernel(uint32_t* bin_hist) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (int i = 0; i < BMPC_TASK_BINS; i++) {
+        uint32_t v = bin_hist[i];
+        bin_hist[i] = acc;
+        acc += v;
+    }
+}
+__global__ void __launch_bounds__(256)
+task_desc_kernel(const uint32_t* off, const uint32_t* toff, uint32_t nb, uint32_t L, uint32_t* bin_cursor,
+                 uint4* desc) {
+    __shared__ uint32_t sh_cnt[BMPC_TASK_BINS];
+    __shared__ uint32_t sh_base[BMPC_TASK_BINS];
+    if (threadIdx.x < BMPC_TASK_BINS) sh_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0, nt = 0, o = 0, t0 = 0, my_full = 0, my_last = 0;
+    if (b < nb) {
+        o = off[b];
+        cnt = off[b + 1] - o;
+        t0 = toff[b];
+        nt = toff[b + 1] - t0;
+        if (nt > 1) my_full = atomicAdd(&sh_cnt[task_bin(L, L)], nt - 1u);
+        if (nt > 0) my_last = atomicAdd(&sh_cnt[task_bin(cnt - (nt - 1u) * L, L)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < BMPC_TASK_BINS) {
+        uint32_t c = sh_cnt[threadIdx.x];
+        sh_base[threadIdx.x] = c ? atomicAdd(bin_cursor + threadIdx.x, c) : 0u;
+    }
+    __syncthreads();
+    if (b < nb && nt > 0) {
+        uint32_t fb = sh_base[task_bin(L, L)] + my_full;
+        for (uint32_t k = 0; k + 1 < nt; k++) desc[fb + k] = make_uint4(o + k * L, L, t0 + k, b);
+        uint32_t last_len = cnt - (nt - 1u) * L;
+        desc[sh_base[task_bin(last_len, L)] + my_last] = make_uint4(o + (nt - 1u) * L, last_len, t0 + nt - 1u, b);
+    }
 }
 
 // buckets whose points were split over more than one accumulate task

@@ -277,13 +277,18 @@ def run_ours(args):
         "note": "integer-pipe bound, not HBM bound: see roofline_int",
     }
     roofline_int = None
+    cw, ww, hh = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib.bmpc_msm_geometry(w.ctx, bases.handle, n, C.byref(cw), C.byref(ww), C.byref(hh))
     if peaks.get("mac32_per_s") and acc_ms:
-        ach = G1_MSM_MAC32_PER_POINT * n / (acc_ms * 1e-3)
+        executed = 10 * 300 * ww.value * n            # 8M+2S mixed additions actually issued
+        ach = executed / (acc_ms * 1e-3)
         roofline_int = {"kernel": "msm_accumulate_kernel<Fp>", "bound": "int32-mac",
                         "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12, "unit": "TMAC32/s",
                         "frac": ach / peaks["mac32_per_s"],
                         "peak_source": "profiles/r01_imad_peak.json (mad.lo.cc/madc.hi.cc chains, measured)",
-                        "model": "48000 MAC32 per point (SURVEY 8d: 16 windows x 10 Fp mul x 300)"}
+                        "work": f"executed: {ww.value} windows of c={cw.value} bits x 10 Fp mul x 300 MAC32 per point",
+                        "survey_model_frac": G1_MSM_MAC32_PER_POINT * n / (acc_ms * 1e-3) / peaks["mac32_per_s"],
+                        "survey_model": "48000 MAC32 per point (SURVEY 8d: fixed 16 windows)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -330,6 +335,40 @@ def run_ours(args):
         except Exception as e:  # keep the headline line even if the secondary workload fails
             line["prove"] = {"error": repr(e)}
 
+    # ---- EvaluationDomain sweep (BASELINE config #3): fft on resident coefficients, GB/s vs HBM peak
+    if world == 1 and not args.no_ntt:
+        ntt = []
+        for logm in range(16, args.ntt_max_log + 1, 2):
+            m = 1 << logm
+            coeffs = torch.from_numpy(rand_limbs(m, 3).view(np.int64)).to(dev)
+            lib.bmpc_ntt_dev(w.ctx, coeffs.data_ptr(), logm, 0, stream)
+            torch.cuda.synchronize()
+            lib.bmpc_ctx_profile(w.ctx, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                st = lib.bmpc_ntt_dev(w.ctx, coeffs.data_ptr(), logm, 0, stream)
+                assert st == 0
+            e1.record()
+            torch.cuda.synchronize()
+            t_ms, cnt = C.c_double(), C.c_uint64()
+            lib.bmpc_ctx_profile_read(w.ctx, 1, C.byref(t_ms), C.byref(cnt))
+            lib.bmpc_ctx_profile(w.ctx, 0)
+            ms_t = e0.elapsed_time(e1) / reps
+            passes = cnt.value // reps
+            pass_ms = t_ms.value / max(cnt.value, 1)
+            butterflies = (m // 2) * logm
+            ntt.append({"log_m": logm, "ms": ms_t, "passes": int(passes),
+                        "algorithmic_gbs": 64 * m / (ms_t * 1e-3) / 1e9,
+                        "hbm_frac": 64 * m / (ms_t * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "pass_kernel_gbs": 64 * m / (pass_ms * 1e-3) / 1e9,
+                        "tmac32_per_s": butterflies * 136 / (ms_t * 1e-3) / 1e12,
+                        "int_frac": (butterflies * 136 / (ms_t * 1e-3) / peaks["mac32_per_s"]) if peaks.get("mac32_per_s") else None})
+            del coeffs
+        line["ntt"] = {"op": "EvaluationDomain::fft, coefficients resident, in place", "sweep": ntt,
+                       "bytes_per_coeff": 64, "mac32_per_butterfly": 136}
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     bases.free()
@@ -350,6 +389,8 @@ def main():
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--ntt-max-log", type=int, default=26)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -125,6 +125,10 @@ int  bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t ba
 int  bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count,
                        uint8_t* out, void* stream);
 size_t bmpc_partial_bytes(int group);
+/* geometry the library will use for an n-point multiexp over `bases` (for reporting work done):
+ * window bits c, number of windows W (point additions per dense point), bucket sets H */
+int  bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t* window_bits,
+                       uint32_t* windows, uint32_t* bucket_sets);
 
 /* ---- EvaluationDomain  (src/domain.rs:21-189) ------------------------------------------ */
 /* from_coeffs (:47-79): pads with zeros to m = 2^exp >= len (m = 1 for len <= 1);

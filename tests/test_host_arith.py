@@ -38,7 +38,7 @@ def test_field_ops(lib, which):
     cases = [(0, 0), (1, 1), (p - 1, p - 1), (p - 1, 1), (R, R)] + [(rng.randrange(p), rng.randrange(p)) for _ in range(500)]
     for a, b in cases:
         out = (ctypes.c_uint32 * n)()
-        for op, e in {0: a * b * Ri % p, 1: (a + b) % p, 2: (a - b) % p, 3: (-a) % p, 5: a * R % p, 6: a * Ri % p}.items():
+        for op, e in {0: a * b * Ri % p, 1: (a + b) % p, 2: (a - b) % p, 3: (-a) % p, 5: a * R % p, 6: a * Ri % p, 7: a * a * Ri % p}.items():
             fn(op, _l(a, n), _l(b, n), out)
             assert _v(out) == e, (which, op)
     for a, _ in cases[1:20]:
