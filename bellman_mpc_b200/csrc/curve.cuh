@@ -93,8 +93,11 @@ struct XYZZ {
         ZZZ = ZZZ * PPP;
     }
 
-    // this += o (complete)
-    BMPC_COLD void add(const XYZZ& o) {
+    // this += o (complete), out of line for cold callers
+    BMPC_COLD void add(const XYZZ& o) { add_inl(o); }
+
+    // this += o (complete), inlined into the bucket-reduction loop
+    BMPC_HD void add_inl(const XYZZ& o) {
         if (o.is_identity()) return;
         if (is_identity()) { *this = o; return; }
         F U1 = X * o.ZZ;

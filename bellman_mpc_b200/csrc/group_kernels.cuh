@@ -133,9 +133,9 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
             uint32_t t0 = __ldg(toff + bidx), t1 = __ldg(toff + bidx + 1);
             if (t1 > t0) {
                 XYZZ<F> v = load_struct(partials + t0);
-                run.add(v);
+                run.add_inl(v);
             }
-            acc.add(run);
+            acc.add_inl(run);
         }
         if (lo != 0) {
             XYZZ<F> m = run.mul(&lo, 1);

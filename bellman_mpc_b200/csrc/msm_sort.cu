@@ -54,12 +54,26 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     p.nb = g.H * g.B;
     p.max_pairs = n * g.W;
     p.max_tasks = p.max_pairs / g.L + p.nb + 1;
-    // reduce: each thread owns S consecutive buckets of one set (S >= 1), blocks of <= 128 threads
-    uint32_t max_tpw = g.H == 1 ? 65536u : 1024u;
-    p.tpw = g.B < max_tpw ? g.B : max_tpw;
-    p.rblock = p.tpw < 128 ? p.tpw : 128;
-    p.S = g.B / p.tpw;
-    p.nblk = p.tpw / p.rblock;
+    // reduce: each thread owns S consecutive buckets of one set.  S is chosen so that all H sets
+    // together fill exactly one wave of resident blocks (a second, nearly empty wave doubled the
+    // kernel time): capacity = SMs x resident 128-thread blocks (3 for G1 at 148 regs, 2 for G2).
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 3 : 2) * 128;
+        size_t total = (size_t)g.H * g.B;
+        uint32_t S = (uint32_t)((total + capacity - 1) / capacity);
+        if (S < 4) S = 4;
+        if (S > g.B) S = g.B;
+        p.S = S;
+        p.tpw = (g.B + S - 1) / S;               // segments (threads) per set
+        p.rblock = 128;
+        if (p.tpw < 128) {                        // power-of-two block for the in-block tree
+            p.rblock = 1;
+            while (p.rblock < p.tpw) p.rblock <<= 1;
+        }
+        p.nblk = (p.tpw + p.rblock - 1) / p.rblock;
+    }
     size_t b = 0;
     size_t nw32 = (n + 31) / 32;
     if (has_density) b += ws_need(nw32 + 1, 4) * 2 + ws_need(scan_chunks_words((uint32_t)nw32), 4);

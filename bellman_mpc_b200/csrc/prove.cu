@@ -38,47 +38,65 @@ __device__ __forceinline__ void encode_compressed(const Affine<F>& p, uint8_t* o
     if (lex_largest(p.y)) out[0] |= 0x20;
 }
 
-__global__ void prove_tail_kernel(ProveTailArgs A) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Stage 1: the seven scalar multiplications of prover.rs:315-343, one thread block each, in
+// parallel (a single thread doing them back to back took 7.5 ms; with full-size r, s it would be
+// ~30 ms).  tmp1: 6 G1 results, tmp2: 1 G2 result.
+//   0 delta1*r   1 delta1*rs   2 alpha*s   3 beta1*r   4 a_answer*s   5 b1_answer*r   | G2: delta2*s
+__global__ void prove_tail_mul_kernel(ProveTailArgs A, G1XYZZ* tmp1, G2XYZZ* tmp2) {
+    if (threadIdx.x != 0) return;
     Fr r = A.rs[0], s = A.rs[1];
-    Fr rs = r * s;                                   // prover.rs:322-323
-    Fr rc = r.from_mont(), sc = s.from_mont(), rsc = rs.from_mont();
-    G1XYZZ alpha = G1XYZZ::from_affine(A.vk_g1[0]);
-    G1XYZZ beta1 = G1XYZZ::from_affine(A.vk_g1[1]);
-    G1XYZZ delta1 = G1XYZZ::from_affine(A.vk_g1[2]);
-    G2XYZZ beta2 = G2XYZZ::from_affine(A.vk_g2[0]);
-    G2XYZZ delta2 = G2XYZZ::from_affine(A.vk_g2[1]);
+    Fr rc = r.from_mont(), sc = s.from_mont(), rsc = (r * s).from_mont();   // :322-323
+    const uint32_t job = blockIdx.x;
+    if (job == 6) {
+        tmp2[0] = G2XYZZ::from_affine(A.vk_g2[1]).mul(sc.l, 8);               // delta_g2 * s :317
+        return;
+    }
+    G1XYZZ base;
+    const uint32_t* k;
+    switch (job) {
+        case 0: base = G1XYZZ::from_affine(A.vk_g1[2]); k = rc.l; break;       // delta_g1 * r  :315
+        case 1: base = G1XYZZ::from_affine(A.vk_g1[2]); k = rsc.l; break;      // delta_g1 * rs :325
+        case 2: base = G1XYZZ::from_affine(A.vk_g1[0]); k = sc.l; break;       // alpha_g1 * s  :326
+        case 3: base = G1XYZZ::from_affine(A.vk_g1[1]); k = rc.l; break;       // beta_g1 * r   :327
+        case 4: base = *A.a_inputs; base.add(*A.a_aux); k = sc.l; break;       // a_answer * s  :331-332
+        default: base = *A.b1_inputs; base.add(*A.b1_aux); k = rc.l; break;    // b1_answer * r :341-342
+    }
+    tmp1[job] = base.mul(k, 8);
+}
 
-    G1XYZZ g_a = delta1.mul(rc.l, 8);                // :315-316
-    g_a.add(alpha);
-    G2XYZZ g_b = delta2.mul(sc.l, 8);                // :317-318
-    g_b.add(beta2);
-    G1XYZZ g_c = delta1.mul(rsc.l, 8);               // :319-327
-    g_c.add(alpha.mul(sc.l, 8));
-    g_c.add(beta1.mul(rc.l, 8));
-
-    G1XYZZ a_answer = *A.a_inputs;                   // :328-332
-    a_answer.add(*A.a_aux);
-    g_a.add(a_answer);
-    g_c.add(a_answer.mul(sc.l, 8));
-
-    G1XYZZ b1_answer = *A.b1_inputs;                 // :334-337
-    b1_answer.add(*A.b1_aux);
-    G2XYZZ b2_answer = *A.b2_inputs;
-    b2_answer.add(*A.b2_aux);
-
-    g_b.add(b2_answer);                              // :339-343
-    g_c.add(b1_answer.mul(rc.l, 8));
-    g_c.add(*A.h);
-    g_c.add(*A.l);
-
-    encode_compressed<Fp>(g_a.to_affine(), A.proof);         // :345-349 + Proof::write
-    encode_compressed<Fp2>(g_b.to_affine(), A.proof + 48);
-    encode_compressed<Fp>(g_c.to_affine(), A.proof + 144);
+// Stage 2: assemble A, B, C (one block each), normalise and compress.
+__global__ void prove_tail_kernel(ProveTailArgs A, const G1XYZZ* tmp1, const G2XYZZ* tmp2) {
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x == 0) {            // A = delta*r + alpha + (a_inputs + a_aux)      :315-316,328-330
+        G1XYZZ g_a = tmp1[0];
+        g_a.add(G1XYZZ::from_affine(A.vk_g1[0]));
+        g_a.add(*A.a_inputs);
+        g_a.add(*A.a_aux);
+        encode_compressed<Fp>(g_a.to_affine(), A.proof);
+    } else if (blockIdx.x == 1) {     // B = delta2*s + beta2 + (b2_inputs + b2_aux)   :317-318,336-339
+        G2XYZZ g_b = tmp2[0];
+        g_b.add(G2XYZZ::from_affine(A.vk_g2[0]));
+        g_b.add(*A.b2_inputs);
+        g_b.add(*A.b2_aux);
+        encode_compressed<Fp2>(g_b.to_affine(), A.proof + 48);
+    } else {                          // C                                              :319-343
+        G1XYZZ g_c = tmp1[1];
+        g_c.add(tmp1[2]);
+        g_c.add(tmp1[3]);
+        g_c.add(tmp1[4]);
+        g_c.add(tmp1[5]);
+        g_c.add(*A.h);
+        g_c.add(*A.l);
+        encode_compressed<Fp>(g_c.to_affine(), A.proof + 144);
+    }
 }
 
 int prove_tail_launch(bmpc_ctx* ctx, const ProveTailArgs& args, cudaStream_t st) {
-    LAUNCH(ctx, prove_tail_kernel, 1, 1, 0, st, args);
+    // scratch for the seven products lives in the context's small device stage (offset 2048)
+    G1XYZZ* tmp1 = reinterpret_cast<G1XYZZ*>(ctx->d_stage + 2048);   // 6 x 192 B
+    G2XYZZ* tmp2 = reinterpret_cast<G2XYZZ*>(ctx->d_stage + 2048 + 1280);   // 384 B
+    LAUNCH(ctx, prove_tail_mul_kernel, 7, 32, 0, st, args, tmp1, tmp2);
+    LAUNCH(ctx, prove_tail_kernel, 3, 32, 0, st, args, (const G1XYZZ*)tmp1, (const G2XYZZ*)tmp2);
     return BMPC_OK;
 }
 

@@ -171,7 +171,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     w = bm.Worker(local)
     lib = w._lib
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default stream: the library treats a NULL stream as "use the context's own stream"
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     n_total = 1 << args.log_n
     n = n_total // world

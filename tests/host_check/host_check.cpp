@@ -11,14 +11,14 @@ void hc_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fr x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
     switch (op) { case 0: z = x * y; break; case 1: z = x + y; break; case 2: z = x - y; break;
         case 3: z = x.neg(); break; case 4: z = x.inv(); break; case 5: z = x.to_mont(); break;
-        case 6: z = x.from_mont(); break; default: z = x.sqr(); }
+        case 6: z = x.from_mont(); break; default: z = x.sqr_redc(); }
     memcpy(r, z.l, 32);
 }
 void hc_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fp x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48);
     switch (op) { case 0: z = x * y; break; case 1: z = x + y; break; case 2: z = x - y; break;
         case 3: z = x.neg(); break; case 4: z = x.inv(); break; case 5: z = x.to_mont(); break;
-        case 6: z = x.from_mont(); break; default: z = x.sqr(); }
+        case 6: z = x.from_mont(); break; default: z = x.sqr_redc(); }
     memcpy(r, z.l, 48);
 }
 void hc_fp2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
