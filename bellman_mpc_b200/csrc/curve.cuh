@@ -38,44 +38,58 @@ struct XYZZ {
     }
     BMPC_HD XYZZ neg() const { return XYZZ{X, Y.neg(), ZZ, ZZZ}; }
 
+    // Every group operation exists in two flavours sharing one body (template on COMPACT):
+    //  * inlined field products -- for the hot bucket-accumulation loop, where the ~7000
+    //    instruction straight-line body streams well because all warps run it in step;
+    //  * COMPACT: every field product is a call of the single out-of-line F::mul_cold.  ncu showed
+    //    the cold kernels (bucket reduction, heavy-bucket combine, final fold, proof tail) starved
+    //    for instructions (stall "no_instruction" 7.7 per issue): with a few divergent warps per SM
+    //    a 130 KB addition body thrashes the 32 KB instruction cache.  The compact bodies are ~1 K
+    //    instructions plus one 10 KB product routine.
+    template <bool COMPACT>
+    BMPC_HD static F M(const F& a, const F& b) {
+        if (COMPACT) return F::mul_cold(a, b);
+        return a * b;
+    }
+
     // 2 * (affine p), p != identity
-    BMPC_COLD static XYZZ dbl_affine(const Affine<F>& p) {
+    template <bool COMPACT>
+    BMPC_HD static XYZZ dbl_affine_impl(const Affine<F>& p) {
         F U = p.y.dbl();
-        F V = U.sqr();
-        F W = U * V;
-        F S = p.x * V;
-        F xx = p.x.sqr();
-        F M = xx.dbl() + xx;
-        F X3 = M.sqr() - S.dbl();
-        F Y3 = M * (S - X3) - W * p.y;
+        F V = M<COMPACT>(U, U);
+        F W = M<COMPACT>(U, V);
+        F S = M<COMPACT>(p.x, V);
+        F xx = M<COMPACT>(p.x, p.x);
+        F Mm = xx.dbl() + xx;
+        F X3 = M<COMPACT>(Mm, Mm) - S.dbl();
+        F Y3 = M<COMPACT>(Mm, S - X3) - M<COMPACT>(W, p.y);
         return XYZZ{X3, Y3, V, W};  // y == 0 gives ZZ == 0 == identity, as it must
     }
+    BMPC_COLD static XYZZ dbl_affine(const Affine<F>& p) { return dbl_affine_impl<true>(p); }
 
     BMPC_COLD XYZZ dbl() const {
         if (is_identity()) return *this;
         F U = Y.dbl();
-        F V = U.sqr();
-        F W = U * V;
-        F S = X * V;
-        F xx = X.sqr();
-        F M = xx.dbl() + xx;
-        F X3 = M.sqr() - S.dbl();
-        F Y3 = M * (S - X3) - W * Y;
-        return XYZZ{X3, Y3, V * ZZ, W * ZZZ};
+        F V = M<true>(U, U);
+        F W = M<true>(U, V);
+        F S = M<true>(X, V);
+        F xx = M<true>(X, X);
+        F Mm = xx.dbl() + xx;
+        F X3 = M<true>(Mm, Mm) - S.dbl();
+        F Y3 = M<true>(Mm, S - X3) - M<true>(W, Y);
+        return XYZZ{X3, Y3, M<true>(V, ZZ), M<true>(W, ZZZ)};
     }
 
-    // out-of-line alias for cold callers
-    BMPC_COLD void add_affine_cold(const Affine<F>& p) { add_affine(p); }
-
-    // this += affine p (complete); inlined into the bucket-accumulation loop
-    BMPC_HD void add_affine(const Affine<F>& p) {
+    // this += affine p (complete)
+    template <bool COMPACT>
+    BMPC_HD void add_affine_impl(const Affine<F>& p) {
         if (p.is_identity()) return;
         if (is_identity()) {
             X = p.x; Y = p.y; ZZ = F::one(); ZZZ = F::one();
             return;
         }
-        F U2 = p.x * ZZ;
-        F S2 = p.y * ZZZ;
+        F U2 = M<COMPACT>(p.x, ZZ);
+        F S2 = M<COMPACT>(p.y, ZZZ);
         F Pd = U2 - X;
         F R = S2 - Y;
         if (Pd.is_zero()) {
@@ -83,27 +97,29 @@ struct XYZZ {
             else *this = identity();
             return;
         }
-        F PP = Pd.sqr();
-        F PPP = Pd * PP;
-        F Q = X * PP;
-        F X3 = R.sqr() - PPP - Q.dbl();
-        Y = R * (Q - X3) - Y * PPP;
+        F PP = M<COMPACT>(Pd, Pd);
+        F PPP = M<COMPACT>(Pd, PP);
+        F Q = M<COMPACT>(X, PP);
+        F X3 = M<COMPACT>(R, R) - PPP - Q.dbl();
+        Y = M<COMPACT>(R, Q - X3) - M<COMPACT>(Y, PPP);
         X = X3;
-        ZZ = ZZ * PP;
-        ZZZ = ZZZ * PPP;
+        ZZ = M<COMPACT>(ZZ, PP);
+        ZZZ = M<COMPACT>(ZZZ, PPP);
     }
+    // inlined into the bucket-accumulation loop
+    BMPC_HD void add_affine(const Affine<F>& p) { add_affine_impl<false>(p); }
+    // out-of-line, compact: cold callers
+    BMPC_COLD void add_affine_cold(const Affine<F>& p) { add_affine_impl<true>(p); }
 
-    // this += o (complete), out of line for cold callers
-    BMPC_COLD void add(const XYZZ& o) { add_inl(o); }
-
-    // this += o (complete), inlined into the bucket-reduction loop
-    BMPC_HD void add_inl(const XYZZ& o) {
+    // this += o (complete)
+    template <bool COMPACT>
+    BMPC_HD void add_impl(const XYZZ& o) {
         if (o.is_identity()) return;
         if (is_identity()) { *this = o; return; }
-        F U1 = X * o.ZZ;
-        F U2 = o.X * ZZ;
-        F S1 = Y * o.ZZZ;
-        F S2 = o.Y * ZZZ;
+        F U1 = M<COMPACT>(X, o.ZZ);
+        F U2 = M<COMPACT>(o.X, ZZ);
+        F S1 = M<COMPACT>(Y, o.ZZZ);
+        F S2 = M<COMPACT>(o.Y, ZZZ);
         F Pd = U2 - U1;
         F R = S2 - S1;
         if (Pd.is_zero()) {
@@ -111,15 +127,17 @@ struct XYZZ {
             else *this = identity();
             return;
         }
-        F PP = Pd.sqr();
-        F PPP = Pd * PP;
-        F Q = U1 * PP;
-        F X3 = R.sqr() - PPP - Q.dbl();
-        Y = R * (Q - X3) - S1 * PPP;
+        F PP = M<COMPACT>(Pd, Pd);
+        F PPP = M<COMPACT>(Pd, PP);
+        F Q = M<COMPACT>(U1, PP);
+        F X3 = M<COMPACT>(R, R) - PPP - Q.dbl();
+        Y = M<COMPACT>(R, Q - X3) - M<COMPACT>(S1, PPP);
         X = X3;
-        ZZ = ZZ * o.ZZ * PP;
-        ZZZ = ZZZ * o.ZZZ * PPP;
+        ZZ = M<COMPACT>(M<COMPACT>(ZZ, o.ZZ), PP);
+        ZZZ = M<COMPACT>(M<COMPACT>(ZZZ, o.ZZZ), PPP);
     }
+    BMPC_COLD void add(const XYZZ& o) { add_impl<true>(o); }      // compact, out of line
+    BMPC_HD void add_inl(const XYZZ& o) { add_impl<false>(o); }    // inlined products
 
     // canonical affine coordinates (one field inversion)
     BMPC_COLD Affine<F> to_affine() const {

@@ -416,7 +416,14 @@ struct Fp2 {
         Fp n = (Fp::mul_cold(c0, c0) + Fp::mul_cold(c1, c1)).inv();
         return Fp2{Fp::mul_cold(c0, n), Fp::mul_cold(c1, n).neg()};
     }
-    BMPC_COLD static Fp2 mul_cold(const Fp2& a, const Fp2& b) { return a * b; }
+    // compact cold product: three calls of the out-of-line Fp product (keeps cold kernels small
+    // enough for the instruction cache -- see curve.cuh)
+    BMPC_COLD static Fp2 mul_cold(const Fp2& a, const Fp2& b) {
+        Fp t0 = Fp::mul_cold(a.c0, b.c0);
+        Fp t1 = Fp::mul_cold(a.c1, b.c1);
+        Fp t2 = Fp::mul_cold(a.c0 + a.c1, b.c0 + b.c1);
+        return Fp2{t0 - t1, t2 - t0 - t1};
+    }
 };
 
 }  // namespace bmpc

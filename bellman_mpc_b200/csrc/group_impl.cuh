@@ -1,6 +1,8 @@
 // Host-side launchers for the curve-typed kernels, instantiated once per group
 // (group_g1.cu: F = Fp, group_g2.cu: F = Fp2).
 #pragma once
+#include <cstdlib>
+
 #include "group_kernels.cuh"
 #include "internal.h"
 
@@ -25,7 +27,12 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
     {
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
-        LAUNCH(ctx, msm_accumulate_kernel<F>, ablocks, 128, 0, st, pts, s.sorted, s.desc, s.ntasks, partials);
+        // BMPC_ACC_COMPACT=1 selects the variant whose field products are calls (smaller code)
+        static const bool compact = getenv("BMPC_ACC_COMPACT") && atoi(getenv("BMPC_ACC_COMPACT")) != 0;
+        if (compact)
+            LAUNCH(ctx, (msm_accumulate_kernel<F, true>), ablocks, 128, 0, st, pts, s.sorted, s.desc, s.ntasks, partials);
+        else
+            LAUNCH(ctx, (msm_accumulate_kernel<F, false>), ablocks, 128, 0, st, pts, s.sorted, s.desc, s.ntasks, partials);
     }
     ProfScope ps_tail(ctx, BMPC_PROF_MSM_REDUCE, st);
     {

@@ -59,7 +59,7 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 // --------------------------------------------------------------------- 4. accumulate
 // One thread per task; a task is a slice of <= L consecutive entries of one bucket in `sorted`,
 // described by desc[t] (built by task_desc_kernel, big tasks first so warps stay balanced).
-template <class F>
+template <class F, bool COMPACT>
 __global__ void __launch_bounds__(128)
 msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint4* desc,
                       const uint32_t* ntasks_p, XYZZ<F>* partials) {
@@ -73,7 +73,7 @@ msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint
         uint32_t e = __ldg(sorted + j);
         Affine<F> p = load_affine<F>(bases + (e & 0x7fffffffu));
         if (e & 0x80000000u) p.y = p.y.neg();
-        acc.add_affine(p);
+        acc.template add_affine_impl<COMPACT>(p);
     }
     store_struct(partials + d.z, acc);
 }
@@ -133,9 +133,9 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
             uint32_t t0 = __ldg(toff + bidx), t1 = __ldg(toff + bidx + 1);
             if (t1 > t0) {
                 XYZZ<F> v = load_struct(partials + t0);
-                run.add_inl(v);
+                run.add(v);
             }
-            acc.add_inl(run);
+            acc.add(run);
         }
         if (lo != 0) {
             XYZZ<F> m = run.mul(&lo, 1);

@@ -54,6 +54,14 @@ def measured_peaks():
             peaks["source"] = "measured"
         except Exception:
             pass
+    kp = os.path.join(ROOT, "profiles", "r01_ncu_kernel_summaries.json")
+    if os.path.exists(kp):
+        try:
+            k = json.load(open(kp))["msm_accumulate_g1"]
+            # ncu --set full capture of this bench command (2^24, 1 GPU): GB read + MB written per launch
+            peaks["acc_traffic_bytes"] = float(k["dram__bytes_read.sum"]) * 1e9 + float(k["dram__bytes_write.sum"]) * 1e6
+        except Exception:
+            pass
     ip = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
     if os.path.exists(ip):
         try:
@@ -275,7 +283,10 @@ def run_ours(args):
         "achieved": G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
         "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": (G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
-        "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
+        "traffic": peaks.get("acc_traffic_bytes") if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+        "traffic_source": "profiles/r01_ncu_kernel_summaries.json (ncu --set full, same command, 1 GPU, 2^24)",
+        "algorithmic_bytes": G1_MSM_BYTES_PER_POINT * n,
+        "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
         "kernel_ms": acc_ms, "share_of_step": acc_ms / ms if ms else None,
         "note": "integer-pipe bound, not HBM bound: see roofline_int",
     }
