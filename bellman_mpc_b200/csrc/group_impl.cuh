@@ -38,7 +38,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     {
         size_t smem = 128 * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_combine_heavy_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ctx, msm_combine_heavy_kernel<F>, 148 * 2, 128, smem, st, s.toff, s.heavy, s.heavy_count, partials);
+        LAUNCH(ctx, msm_combine_heavy_kernel<F>, 148 * 3, 128, smem, st, s.toff, s.heavy, s.heavy_count, partials);
     }
     {
         size_t smem = (size_t)p.rblock * sizeof(XYZZ<F>);

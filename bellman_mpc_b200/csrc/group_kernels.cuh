@@ -79,37 +79,42 @@ msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint
 }
 
 // ------------------------------------------------------------------ 5. heavy buckets
-// one warp per heavy bucket: partials[toff[b]] <- sum of the bucket's partials
+// One block per heavy bucket (grid-stride over the list): partials[toff[b]] <- sum of the
+// bucket's partial sums.  Typical heavy buckets hold 2..30 partials (the over-full low buckets of
+// the top window); 0/1-heavy witnesses produce a few buckets with thousands, which the 128
+// threads fold in strides before the shared-memory tree.
 template <class F>
 __global__ void __launch_bounds__(128)
 msm_combine_heavy_kernel(const uint32_t* toff, const uint32_t* heavy_list,
                          const uint32_t* heavy_count, XYZZ<F>* partials) {
     extern __shared__ uint4 heavy_smem[];
-    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_smem) + (threadIdx.x & ~31u);
-    uint32_t lane = threadIdx.x & 31;
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t nh = *heavy_count;
-    for (uint32_t h = warp; h < nh; h += nwarps) {
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_smem);
+    const uint32_t nh = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
         uint32_t t0 = toff[b], t1 = toff[b + 1];
-        XYZZ<F> acc = XYZZ<F>::identity();
-        for (uint32_t t = t0 + lane; t < t1; t += 32) {
-            XYZZ<F> v = load_struct(partials + t);
-            acc.add(v);
-        }
-        sm[lane] = acc;
-        __syncwarp();
-        for (uint32_t s = 16; s > 0; s >>= 1) {
-            if (lane < s) {
-                XYZZ<F> x = sm[lane], y = sm[lane + s];
-                x.add(y);
-                sm[lane] = x;
+        uint32_t k = t1 - t0;
+        uint32_t width = 1;                      // power of two >= min(k, 128)
+        while (width < k && width < 128u) width <<= 1;
+        if (threadIdx.x < width) {
+            XYZZ<F> acc = XYZZ<F>::identity();
+            for (uint32_t t = t0 + threadIdx.x; t < t1; t += 128u) {
+                XYZZ<F> v = load_struct(partials + t);
+                acc.add(v);
             }
-            __syncwarp();
+            sm[threadIdx.x] = acc;
         }
-        if (lane == 0) store_struct(partials + t0, sm[0]);
-        __syncwarp();
+        __syncthreads();
+        for (uint32_t st = width >> 1; st > 0; st >>= 1) {
+            if (threadIdx.x < st) {
+                XYZZ<F> x = sm[threadIdx.x], y = sm[threadIdx.x + st];
+                x.add(y);
+                sm[threadIdx.x] = x;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_struct(partials + t0, sm[0]);
+        __syncthreads();
     }
 }
 

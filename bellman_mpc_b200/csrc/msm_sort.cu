@@ -16,15 +16,36 @@ static inline size_t scan_chunks_words(uint32_t n) {
     return (n + BMPC_SCAN_CHUNK - 1) / BMPC_SCAN_CHUNK + 2;
 }
 
+// Bits of the scalar that fall into the top window: 255 - c (W - 1).  When this is small every
+// point drops its top digit into the same handful of buckets (c = 21: 3 bits -> 5 buckets with
+// n / 5 points each; c dividing 255: only the carry, one bucket) -- hot atomics in the sort and
+// thousands of partial sums to fold.  Window sizes with fewer than MIN_TOP_BITS are never chosen.
+static inline uint32_t top_window_bits(uint32_t c) { return 255u - c * (255u / c); }
+constexpr uint32_t MIN_TOP_BITS = 7;
+
+// Cost model in point additions: n W mixed additions + 2.8 full additions per bucket.
+static uint32_t pick_window(size_t n, uint32_t lo, uint32_t hi, bool one_bucket_set) {
+    uint32_t best = 0;
+    double best_cost = 0;
+    for (uint32_t c = lo; c <= hi; c++) {
+        if (n >= (1u << 16) && top_window_bits(c) < MIN_TOP_BITS) continue;  // small n: harmless
+        uint32_t W = 255 / c + 1;
+        double buckets = (double)(one_bucket_set ? 1u : W) * (double)(1u << (c - 1));
+        double cost = (double)n * W + 2.8 * 1.4 * buckets;
+        if (!best || cost < best_cost) { best = c; best_cost = cost; }
+    }
+    return best ? best : lo;
+}
+
 // Window bits for precomputed tables: all windows share one bucket set, so the bucket count can
-// grow until the (parallel) bucket reduction matters: 2^(c-1) ~ n / 8.
+// grow until the (parallel) bucket reduction matters.
 uint32_t msm_table_window(size_t n_bases) {
     uint32_t lg = 0;
     while (((size_t)1 << (lg + 1)) <= n_bases) lg++;
-    uint32_t c = lg > 6 ? lg - 2 : 4;
-    if (c > 22) c = 22;
-    if (c < 4) c = 4;
-    return c;
+    uint32_t hi = lg > 5 ? lg - 1 : 4, lo = lg > 9 ? lg - 5 : 4;
+    if (hi > 22) hi = 22;
+    if (lo > hi) lo = hi;
+    return pick_window(n_bases, lo, hi, true);
 }
 
 MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density) {
@@ -37,8 +58,10 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     else {
         uint32_t lg = 0;
         while (((size_t)1 << (lg + 1)) <= n) lg++;
-        c = lg > 8 ? lg - 4 : 4;
-        if (c > 16) c = 16;
+        uint32_t hi = lg > 8 ? lg - 3 : 5, lo = lg > 10 ? lg - 6 : 4;
+        if (hi > 16) hi = 16;
+        if (lo > hi) lo = hi;
+        c = pick_window(n, lo, hi, false);
     }
     if (c < 2) c = 2;
     if (c > 22) c = 22;

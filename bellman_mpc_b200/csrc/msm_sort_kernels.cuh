@@ -45,18 +45,19 @@ __device__ __forceinline__ bool resolve_base(const MsmInput& in, size_t i, uint3
     return true;
 }
 
-// Shared by count and scatter: calls f(window, bucket_in_window, negative) for every non-zero
-// signed digit.  Returns false when the position contributes nothing.
-template <class Fn>
-__device__ __forceinline__ bool for_each_digit(const MsmInput& in, const MsmGeom& g, size_t i,
-                                               uint32_t* flags, bool raise, uint32_t& base_idx,
-                                               Fn f) {
+// Shared prologue of count and scatter: resolves the base, applies the reference's skip /
+// EOF / identity rules and loads the scalar.  Returns false when the position contributes
+// nothing (the caller keeps running with `alive == false`: both kernels use full-warp
+// match_any, so no lane may leave early).
+__device__ __forceinline__ bool msm_prepare(const MsmInput& in, const MsmGeom& g, size_t i,
+                                            uint32_t* flags, bool raise, uint32_t& base_idx,
+                                            uint32_t s[8]) {
+    if (i >= in.n) return false;
     if (!resolve_base(in, i, base_idx)) return false;
     if (base_idx >= in.bases_len) {  // Source::{next,skip} -> UnexpectedEof (multiexp.rs:55-61,74-80)
         if (raise) atomicOr(flags, (uint32_t)MSM_FLAG_EOF);
         return false;
     }
-    uint32_t s[8];
     load_scalar(in.scalars + i * 8, s);
     if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return false;  // skip(1)
     if ((__ldg(in.inf_bitmap + (base_idx >> 5)) >> (base_idx & 31)) & 1u) {
@@ -69,67 +70,64 @@ __device__ __forceinline__ bool for_each_digit(const MsmInput& in, const MsmGeom
         }
         return false;
     }
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (g.c - 1);
-    for (uint32_t w = 0; w < g.W; w++) {
-        uint32_t d = get_bits(s, w * g.c, g.c) + carry;
-        bool neg = d > half;
-        if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
-        // window w -> bucket set (w % H), table (w / H): with precomputed tables H == 1 and
-        // every window adds table_w[i] = 2^(c w) P_i into the same bucket set
-        if (d != 0) f(w, d - 1u, neg);
-    }
     return true;
 }
 
-__global__ void msm_count_kernel(MsmInput in, MsmGeom g, uint32_t* hist, uint32_t* flags) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= in.n) return;
-    uint32_t base_idx;
-    for_each_digit(in, g, i, flags, true, base_idx,
-                   [&](uint32_t w, uint32_t b, bool) { atomicAdd(hist + (size_t)(w % g.H) * g.B + b, 1u); });
+// Warp-aggregated atomicAdd: lanes of the warp holding the same key are grouped with
+// match.any, one lane adds the group size and every lane gets base + its rank in the group.
+// With uniform scalars groups are singletons; with 0/1-heavy witnesses (most lanes hit the same
+// bucket) it removes the same-address serialisation in L2.  Must be called by all 32 lanes;
+// dead lanes pass live = false.
+__device__ __forceinline__ uint32_t warp_agg_add(uint32_t* counters, uint32_t key, bool live, bool want_pos) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t k = live ? key : (0xffffffe0u + lane);       // unique dummy keys for dead lanes
+    uint32_t grp = __match_any_sync(0xffffffffu, k);
+    uint32_t leader = __ffs(grp) - 1u;
+    uint32_t base = 0;
+    if (live && lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(grp));
+    if (!want_pos) return 0;
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(grp & ((1u << lane) - 1u));
 }
 
-// Scatter: the slot of each (position, window) pair comes back from an atomicAdd; the returning
-// atomics of GROUP windows are issued back to back so their L2 round trips overlap, then the
-// GROUP stores go out.
-__global__ void msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uint32_t* sorted) {
+// window w -> bucket set (w % H), table (w / H): with precomputed tables H == 1 and every window
+// adds table_w[i] = 2^(c w) P_i into the same bucket set.
+__global__ void __launch_bounds__(256)
+msm_count_kernel(MsmInput in, MsmGeom g, uint32_t* hist, uint32_t* flags) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= in.n) return;
-    uint32_t base_idx;
-    if (!resolve_base(in, i, base_idx)) return;
-    if (base_idx >= in.bases_len) return;
-    uint32_t s[8];
-    load_scalar(in.scalars + i * 8, s);
-    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
-    if ((__ldg(in.inf_bitmap + (base_idx >> 5)) >> (base_idx & 31)) & 1u) return;
-    constexpr int GROUP = 4;
+    uint32_t base_idx = 0, s[8];
+    bool alive = msm_prepare(in, g, i, flags, true, base_idx, s);
     uint32_t carry = 0;
     const uint32_t half = 1u << (g.c - 1);
-    for (uint32_t w0 = 0; w0 < g.W; w0 += GROUP) {
-        uint32_t key[GROUP], val[GROUP], pos[GROUP];
-        bool live[GROUP];
-#pragma unroll
-        for (int j = 0; j < GROUP; j++) {
-            uint32_t w = w0 + j;
-            live[j] = false;
-            if (w < g.W) {
-                uint32_t d = get_bits(s, w * g.c, g.c) + carry;
-                bool neg = d > half;
-                if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
-                if (d != 0) {
-                    live[j] = true;
-                    key[j] = (w % g.H) * g.B + (d - 1u);
-                    val[j] = (base_idx + (w / g.H) * g.tab_stride) | (neg ? 0x80000000u : 0u);
-                }
-            }
+    for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t d = 0;
+        if (alive) {
+            d = get_bits(s, w * g.c, g.c) + carry;
+            if (d > half) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
         }
-#pragma unroll
-        for (int j = 0; j < GROUP; j++)
-            if (live[j]) pos[j] = atomicAdd(cursor + key[j], 1u);
-#pragma unroll
-        for (int j = 0; j < GROUP; j++)
-            if (live[j]) sorted[pos[j]] = val[j];
+        warp_agg_add(hist, (w % g.H) * g.B + (d - 1u), alive && d != 0, false);
+    }
+}
+
+// Scatter: the slot of each (position, window) pair comes back from the (aggregated) atomicAdd.
+__global__ void __launch_bounds__(256)
+msm_scatter_kernel(MsmInput in, MsmGeom g, uint32_t* cursor, uint32_t* sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t base_idx = 0, s[8];
+    bool alive = msm_prepare(in, g, i, nullptr, false, base_idx, s);
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (g.c - 1);
+    for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t d = 0;
+        bool neg = false;
+        if (alive) {
+            d = get_bits(s, w * g.c, g.c) + carry;
+            neg = d > half;
+            if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
+        }
+        bool live = alive && d != 0;
+        uint32_t pos = warp_agg_add(cursor, (w % g.H) * g.B + (d - 1u), live, true);
+        if (live) sorted[pos] = (base_idx + (w / g.H) * g.tab_stride) | (neg ? 0x80000000u : 0u);
     }
 }
 

@@ -164,6 +164,11 @@ def run_reference(args):
 
 # -------------------------------------------------------------------------------- our arm
 def run_ours(args):
+    # Everything that libraries print to stdout (e.g. NCCL's version banner) goes to stderr;
+    # the real stdout is restored only for the one JSON line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -383,6 +388,8 @@ def run_ours(args):
         line["ntt"] = {"op": "EvaluationDomain::fft, coefficients resident, in place", "sweep": ntt,
                        "bytes_per_coeff": 64, "mac32_per_butterfly": 136}
 
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     bases.free()

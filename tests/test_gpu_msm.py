@@ -243,3 +243,30 @@ def test_large_known_dlog(worker):
     dot = sum(k * s for k, s in zip(ks, sc)) % Q
     assert got == G.to_uncompressed(G.mul(G.gen, dot))
     bases.free()
+
+
+@pytest.mark.parametrize("tables", [False, True])
+def test_hot_buckets_large(worker, tables):
+    """boolean-heavy witness shape at 2^18 (SURVEY 8d/4 secondary profile): 35 % zeros, 35 % ones,
+    10 % small values, 20 % uniform -- a few buckets receive a large share of the points (task
+    splitting, heavy-bucket combine, warp-aggregated atomics); checked against sum k_i s_i"""
+    from oracle import cref
+    n = 1 << 18
+    rs = np.random.RandomState(77)
+    ks = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    sc = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
+    kind = rs.randint(0, 100, size=n)
+    sc[kind < 35] = 0
+    ones = (kind >= 35) & (kind < 70)
+    sc[ones] = 0
+    sc[ones, 0] = 1
+    small = (kind >= 70) & (kind < 80)
+    sc[small, 1:] = 0
+    sc[small, 0] &= np.uint64(0xFFFF)
+    G = curves.G1
+    bases = bm.Bases.fixed_base_mul(worker, bm.G1, G.to_uncompressed(G.gen), ks)
+    if tables:
+        bases.precompute()
+    got = bm.multiexp(worker, (bases, 0), bm.FullDensity(), sc).wait()
+    assert got == cref.g1_generator_mul(cref.fr_dot(ks, sc))
+    bases.free()
