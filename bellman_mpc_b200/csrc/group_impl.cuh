@@ -3,8 +3,8 @@
 #pragma once
 #include <cstdlib>
 
-#include "group_kernels.cuh"
 #include "internal.h"
+#include "group_kernels.cuh"
 
 namespace bmpc {
 

@@ -137,8 +137,12 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
             uint32_t bidx = w * B + lo + j - 1u;  // digit magnitude lo + j
             uint32_t t0 = __ldg(toff + bidx), t1 = __ldg(toff + bidx + 1);
             if (t1 > t0) {
-                XYZZ<F> v = load_struct(partials + t0);
-                run.add(v);
+                // few partial sums: fold them here; many: the heavy combine left the total in slot t0
+                uint32_t k = (t1 - t0 <= BMPC_INLINE_PARTIALS) ? (t1 - t0) : 1u;
+                for (uint32_t q = 0; q < k; q++) {
+                    XYZZ<F> v = load_struct(partials + t0 + q);
+                    run.add(v);
+                }
             }
             acc.add(run);
         }

@@ -185,6 +185,9 @@ void ntt_free_tables(bmpc_ctx* ctx);
 
 // ------------------------------------------------------------- msm_sort.cu
 enum { MSM_FLAG_EOF = 1, MSM_FLAG_IDENT_ANY = 2, MSM_FLAG_IDENT_TOP = 4 };
+// a bucket with at most this many partial sums is folded inline by the reduce kernel; more go
+// through the heavy-bucket combine first (which leaves the total in the first slot)
+#define BMPC_INLINE_PARTIALS 4u
 
 struct MsmGeom {
     uint32_t c;        // window bits

@@ -289,12 +289,13 @@ task_desc_kernel(const uint32_t* off, const uint32_t* toff, uint32_t nb, uint32_
     }
 }
 
-// buckets whose points were split over more than one accumulate task
+// buckets whose points were split over more than BMPC_INLINE_PARTIALS accumulate tasks
 __global__ void msm_find_heavy_kernel(const uint32_t* toff, uint32_t nb, uint32_t* heavy_list,
                                       uint32_t* heavy_count) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    if (toff[b + 1] - toff[b] > 1u) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+    // up to BMPC_INLINE_PARTIALS partial sums are folded by the reduce kernel itself
+    if (toff[b + 1] - toff[b] > BMPC_INLINE_PARTIALS) heavy_list[atomicAdd(heavy_count, 1u)] = b;
 }
 
 }  // namespace bmpc
