@@ -10,7 +10,10 @@ namespace bmpc {
 
 template <class F>
 size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
-    return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.g.H * p.nblk, sizeof(XYZZ<F>)) + 1024;
+    size_t b = ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.red_H * p.nblk, sizeof(XYZZ<F>)) + 1024;
+    if (p.use2d)
+        b += ws_need((size_t)p.g.H * 2 * p.NT, sizeof(XYZZ<F>)) + ws_need((size_t)p.red_H * p.Bm, sizeof(XYZZ<F>));
+    return b;
 }
 
 template <class F>
@@ -18,8 +21,14 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
                             int mode, uint8_t* d_out_bytes, void* d_out_xyzz, cudaStream_t st) {
     const MsmGeom& g = p.g;
     XYZZ<F>* partials = ws_take<XYZZ<F>>(ctx, p.max_tasks);
-    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
-    if (!partials || !blk_out) {
+    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)p.red_H * p.nblk);
+    XYZZ<F>* rc_part = nullptr;
+    XYZZ<F>* rc_sums = nullptr;
+    if (p.use2d) {
+        rc_part = ws_take<XYZZ<F>>(ctx, (size_t)g.H * 2 * p.NT);
+        rc_sums = ws_take<XYZZ<F>>(ctx, (size_t)p.red_H * p.Bm);
+    }
+    if (!partials || !blk_out || (p.use2d && (!rc_part || !rc_sums))) {
         ctx->err = "msm workspace carve failed (curve)";
         return BMPC_ERR_INVALID;
     }
@@ -44,14 +53,24 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
         size_t smem = (size_t)p.rblock * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(128 * sizeof(XYZZ<F>))));
-        dim3 grid(p.nblk, g.H);
-        LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, partials, s.toff, g.B, p.S, blk_out);
+        dim3 grid(p.nblk, p.red_H);
+        if (p.use2d) {
+            dim3 g1((2 * p.NT + 127) / 128, g.H), g2((2 * p.Bm + 127) / 128, g.H);
+            LAUNCH(ctx, msm_rowcol_kernel<F>, g1, 128, 0, st, (const XYZZ<F>*)partials, s.toff, g.B, p.logC, p.S2, rc_part);
+            LAUNCH(ctx, msm_rowcol_fold_kernel<F>, g2, 128, 0, st, (const XYZZ<F>*)rc_part, g.B, p.logC, p.S2, p.Bm, rc_sums);
+            LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, (const XYZZ<F>*)rc_sums, (const uint32_t*)nullptr,
+                   p.red_B, p.S, blk_out);
+        } else {
+            LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, (const XYZZ<F>*)partials, s.toff, g.B, p.S, blk_out);
+        }
     }
     {
-        size_t smem = (size_t)(BMPC_FINAL_THREADS + g.H) * sizeof(XYZZ<F>);
+        size_t smem = (size_t)(BMPC_FINAL_THREADS + p.red_H) * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ctx, msm_final_kernel<F>, 1, BMPC_FINAL_THREADS, smem, st, blk_out, g.H, p.nblk, g.c, mode,
-               d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        // doublings before adding an even / odd set (see msm_final_kernel)
+        uint32_t into_even = p.use2d ? p.logC : g.c, into_odd = p.use2d ? g.c - p.logC : g.c;
+        LAUNCH(ctx, msm_final_kernel<F>, 1, BMPC_FINAL_THREADS, smem, st, blk_out, p.red_H, p.nblk, into_even,
+               into_odd, mode, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     }
     return BMPC_OK;
 }

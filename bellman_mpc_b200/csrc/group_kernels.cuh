@@ -119,8 +119,85 @@ msm_combine_heavy_kernel(const uint32_t* toff, const uint32_t* heavy_list,
 }
 
 // ------------------------------------------------------------------- 6. window reduce
-// grid = (segments_per_window / blockDim, W).  Thread handles S consecutive buckets with digit
-// magnitudes lo+1 .. lo+S:  sum v B_v = sum (v - lo) B_v + lo * sum B_v.
+// Sum of a bucket's partial sums: few -> folded here; many -> the heavy combine left the total
+// in the first slot.
+template <class F>
+__device__ __forceinline__ XYZZ<F> bucket_value(const XYZZ<F>* partials, const uint32_t* toff, uint32_t bidx) {
+    uint32_t t0 = __ldg(toff + bidx), t1 = __ldg(toff + bidx + 1);
+    XYZZ<F> v = XYZZ<F>::identity();
+    if (t1 > t0) {
+        v = load_struct(partials + t0);
+        uint32_t k = (t1 - t0 <= BMPC_INLINE_PARTIALS) ? (t1 - t0) : 1u;
+        for (uint32_t q = 1; q < k; q++) {
+            XYZZ<F> u = load_struct(partials + t0 + q);
+            v.add(u);
+        }
+    }
+    return v;
+}
+
+// 6a. Two-dimensional bucket reduction.  With bucket index = r C + col (C = 2^logC columns),
+//   sum_v v B_v = C * sum_r r RowSum_r + sum_col (col + 1) ColSum_col,
+// so the weighted sum over 2^(c-1) buckets becomes two PLAIN sums per bucket (no running-sum
+// dependency, no per-thread scalar multiplication) plus weighted sums over only R + C elements.
+// Thread t < NT sums S consecutive buckets of one row; thread NT + t' sums S rows of one column
+// (consecutive threads -> consecutive columns -> coalesced).  grid = (2 NT / 128, H).
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_rowcol_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uint32_t logC, uint32_t S,
+                  XYZZ<F>* P) {
+    const uint32_t h = blockIdx.y, C = 1u << logC, NT = B / S;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * NT) return;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (t < NT) {
+        uint32_t base = h * B + t * S;
+        for (uint32_t q = 0; q < S; q++) {
+            XYZZ<F> v = bucket_value<F>(partials, toff, base + q);
+            acc.add(v);
+        }
+    } else {
+        uint32_t tt = t - NT, col = tt & (C - 1u), i = tt >> logC;
+        uint32_t base = h * B + i * S * C + col;
+        for (uint32_t q = 0; q < S; q++) {
+            XYZZ<F> v = bucket_value<F>(partials, toff, base + q * C);
+            acc.add(v);
+        }
+    }
+    store_struct(P + (size_t)h * 2 * NT + t, acc);
+}
+// 6b. RowSum / ColSum from the partial sums.  Output E holds 2 H sets of Bm entries: set 2h = the
+// columns of bucket set h (weight col + 1), set 2h + 1 = its rows 1 .. R-1 (weight r); unused
+// entries are the identity.  grid = (2 Bm / 128, H).
+template <class F>
+__global__ void __launch_bounds__(128)
+msm_rowcol_fold_kernel(const XYZZ<F>* P, uint32_t B, uint32_t logC, uint32_t S, uint32_t Bm, XYZZ<F>* E) {
+    const uint32_t h = blockIdx.y, C = 1u << logC, R = B >> logC, NT = B / S;
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * Bm) return;
+    const XYZZ<F>* Ph = P + (size_t)h * 2 * NT;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (e < Bm) {
+        if (e < C)
+            for (uint32_t i = 0; i < R / S; i++) {
+                XYZZ<F> v = load_struct(Ph + NT + (size_t)i * C + e);
+                acc.add(v);
+            }
+    } else {
+        uint32_t r = e - Bm + 1u;
+        if (r < R)
+            for (uint32_t j = 0; j < C / S; j++) {
+                XYZZ<F> v = load_struct(Ph + (size_t)r * (C / S) + j);
+                acc.add(v);
+            }
+    }
+    store_struct(E + (size_t)(2 * h) * Bm + e, acc);
+}
+
+// 6c. Weighted sum of one set: sum_k (k + 1) X_k.  Each thread owns S consecutive entries
+// (running sums + lo * sum correction), block tree in shared memory.  toff == NULL: X is the plain
+// array `partials` (the row/column sums of 6b); otherwise X_k = bucket k through toff.
+// grid = (blocks per set, number of sets).
 template <class F>
 __global__ void __launch_bounds__(128)
 msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uint32_t S,
@@ -134,16 +211,9 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
     if (lo < B) {
         uint32_t cnt = (B - lo < S) ? (B - lo) : S;
         for (uint32_t j = cnt; j > 0; j--) {
-            uint32_t bidx = w * B + lo + j - 1u;  // digit magnitude lo + j
-            uint32_t t0 = __ldg(toff + bidx), t1 = __ldg(toff + bidx + 1);
-            if (t1 > t0) {
-                // few partial sums: fold them here; many: the heavy combine left the total in slot t0
-                uint32_t k = (t1 - t0 <= BMPC_INLINE_PARTIALS) ? (t1 - t0) : 1u;
-                for (uint32_t q = 0; q < k; q++) {
-                    XYZZ<F> v = load_struct(partials + t0 + q);
-                    run.add(v);
-                }
-            }
+            uint32_t bidx = w * B + lo + j - 1u;  // weight lo + j
+            XYZZ<F> v = toff ? bucket_value<F>(partials, toff, bidx) : load_struct(partials + bidx);
+            run.add(v);
             acc.add(run);
         }
         if (lo != 0) {
@@ -165,16 +235,16 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
 }
 
 // ------------------------------------------------------------------------ 7. final
-// blk_out[H][nblk] -> per-set sums (block tree) -> Horner over the H bucket sets (c doublings
-// per set, multiexp.rs:244-249; H == 1 with precomputed tables: no doublings at all).
+// blk_out[H][nblk] -> per-set sums (block tree) -> Horner over the sets (the doubling fold of
+// multiexp.rs:244-249; with precomputed tables only the log2(C) doublings of the 2-D reduction).
 // mode 0: canonical affine, uncompressed big-endian bytes to out_bytes
 // mode 1: leave the XYZZ partial in out_xyzz (sharded MSM)
 // Launch: 1 block of FINAL_THREADS threads, dynamic smem = (FINAL_THREADS + H) * sizeof(XYZZ).
 #define BMPC_FINAL_THREADS 64
 template <class F>
 __global__ void __launch_bounds__(BMPC_FINAL_THREADS)
-msm_final_kernel(const XYZZ<F>* blk_out, uint32_t H, uint32_t nblk, uint32_t c,
-                 int mode, uint8_t* out_bytes, XYZZ<F>* out_xyzz) {
+msm_final_kernel(const XYZZ<F>* blk_out, uint32_t H, uint32_t nblk, uint32_t dbl_into_even,
+                 uint32_t dbl_into_odd, int mode, uint8_t* out_bytes, XYZZ<F>* out_xyzz) {
     extern __shared__ uint4 final_smem[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(final_smem);
     XYZZ<F>* win = sm + BMPC_FINAL_THREADS;
@@ -199,9 +269,14 @@ msm_final_kernel(const XYZZ<F>* blk_out, uint32_t H, uint32_t nblk, uint32_t c,
     }
     if (threadIdx.x != 0) return;
     XYZZ<F> acc = XYZZ<F>::identity();
+    // Horner from the top set down: before adding set h the accumulator is doubled
+    // dbl_into_even (h even) or dbl_into_odd (h odd) times.  One-dimensional reduction: both = c.
+    // Two-dimensional: sets come in (columns, rows) pairs, rows weigh 2^logC, pairs 2^c apart.
     for (int h = (int)H - 1; h >= 0; h--) {
-        if (h != (int)H - 1)
-            for (uint32_t j = 0; j < c; j++) acc = acc.dbl();
+        if (h != (int)H - 1) {
+            uint32_t nd = (h & 1) ? dbl_into_odd : dbl_into_even;
+            for (uint32_t j = 0; j < nd; j++) acc = acc.dbl();
+        }
         XYZZ<F> v = win[h];
         acc.add(v);
     }

@@ -204,7 +204,11 @@ struct MsmPlan {
     MsmGeom g;
     uint32_t nb;  // total buckets
     size_t max_pairs, max_tasks;
-    uint32_t tpw, rblock, S, nblk;
+    uint32_t tpw, rblock, S, nblk;   // weighted-sum kernel geometry (per set of `red_B` entries)
+    // two-dimensional bucket reduction (use2d): buckets of a set form R x C, C = 2^logC
+    bool use2d;
+    uint32_t logC, S2, NT, Bm;       // S2 buckets per row/col thread, NT = B / S2, Bm = max(R, C)
+    uint32_t red_H, red_B;           // sets / entries per set seen by the weighted-sum kernel
     size_t sort_bytes;  // scratch for everything except the curve-typed buffers
 };
 

@@ -2,6 +2,7 @@
 // counting-sort scatter.  Reference: src/multiexp.rs:191-223 (the per-window scan that this
 // replaces) and :254-281 (window rule, density length).
 #include <cmath>
+#include <cstdlib>
 
 #include "msm_sort_kernels.cuh"
 
@@ -84,12 +85,31 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
         size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 3 : 2) * 128;
-        size_t total = (size_t)g.H * g.B;
+        // two-dimensional reduction for big bucket sets (see msm_rowcol_kernel)
+        // Measured on B200 (2^19 buckets: 1-D 3.35 ms vs 2-D 4.2 ms; 2^21: 6.76 vs 6.73) it does not
+        // beat the running-sum kernel yet, so it is opt-in: BMPC_REDUCE_2D=1.
+        p.use2d = g.B >= 4096 && getenv("BMPC_REDUCE_2D") && atoi(getenv("BMPC_REDUCE_2D")) != 0;
+        p.red_H = g.H;
+        p.red_B = g.B;
+        p.logC = p.S2 = p.NT = p.Bm = 0;
+        if (p.use2d) {
+            p.logC = (g.c - 1) / 2;                       // C = 2^logC <= R
+            uint32_t C = 1u << p.logC, R = g.B >> p.logC;
+            size_t want = ((size_t)2 * g.H * g.B + capacity - 1) / capacity;   // one wave of threads
+            uint32_t S2 = 4;
+            while (S2 < want && S2 < C) S2 <<= 1;
+            p.S2 = S2;
+            p.NT = g.B / S2;
+            p.Bm = R > C ? R : C;
+            p.red_H = 2 * g.H;
+            p.red_B = p.Bm;
+        }
+        size_t total = (size_t)p.red_H * p.red_B;
         uint32_t S = (uint32_t)((total + capacity - 1) / capacity);
         if (S < 4) S = 4;
-        if (S > g.B) S = g.B;
+        if (S > p.red_B) S = p.red_B;
         p.S = S;
-        p.tpw = (g.B + S - 1) / S;               // segments (threads) per set
+        p.tpw = (p.red_B + S - 1) / S;           // segments (threads) per set
         p.rblock = 128;
         if (p.tpw < 128) {                        // power-of-two block for the in-block tree
             p.rblock = 1;

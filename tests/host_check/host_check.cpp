@@ -6,19 +6,19 @@
 using namespace bmpc;
 
 extern "C" {
-// op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 sqr
+// op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 sqr, 8 inv_fermat
 void hc_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fr x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32);
     switch (op) { case 0: z = x * y; break; case 1: z = x + y; break; case 2: z = x - y; break;
         case 3: z = x.neg(); break; case 4: z = x.inv(); break; case 5: z = x.to_mont(); break;
-        case 6: z = x.from_mont(); break; default: z = x.sqr_redc(); }
+        case 6: z = x.from_mont(); break; case 8: z = x.inv_fermat(); break; default: z = x.sqr_redc(); }
     memcpy(r, z.l, 32);
 }
 void hc_fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fp x, y, z; memcpy(x.l, a, 48); memcpy(y.l, b, 48);
     switch (op) { case 0: z = x * y; break; case 1: z = x + y; break; case 2: z = x - y; break;
         case 3: z = x.neg(); break; case 4: z = x.inv(); break; case 5: z = x.to_mont(); break;
-        case 6: z = x.from_mont(); break; default: z = x.sqr_redc(); }
+        case 6: z = x.from_mont(); break; case 8: z = x.inv_fermat(); break; default: z = x.sqr_redc(); }
     memcpy(r, z.l, 48);
 }
 void hc_fp2_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
