@@ -47,6 +47,10 @@ class PolynomialDegreeTooLarge(SynthesisError):
     pass
 
 
+class InvalidData(IoError):
+    """io::ErrorKind::InvalidData from Parameters::read ("invalid G1", "point at infinity")"""
+
+
 def _raise(status, ctx=None):
     if status == _lib.OK:
         return
@@ -56,6 +60,8 @@ def _raise(status, ctx=None):
         raise UnexpectedEof("expected more bases from source")
     if status == _lib.ERR_DEGREE_TOO_LARGE:
         raise PolynomialDegreeTooLarge()
+    if status == _lib.ERR_INVALID_DATA:
+        raise InvalidData(_lib.load().bmpc_last_error(ctx).decode() if ctx is not None else "invalid data")
     if status == _lib.ERR_LENGTH_MISMATCH:
         raise AssertionError("length mismatch")        # the reference panics (assert!)
     msg = ""
@@ -395,6 +401,40 @@ class Parameters:
         self.h, self.l, self.a, self.b_g1, self.b_g2 = h, l, a, b_g1, b_g2
         self.alpha_g1, self.beta_g1, self.beta_g2 = bytes(alpha_g1), bytes(beta_g1), bytes(beta_g2)
         self.delta_g1, self.delta_g2 = bytes(delta_g1), bytes(delta_g2)
+
+    @staticmethod
+    def read(worker, data, checked):
+        """Parameters::read(reader, checked) (groth16/mod.rs:292-400): decode + validate on the GPU,
+        query vectors stay resident."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        pf = _lib.ParametersFile()
+        _raise(worker._lib.bmpc_params_read(worker.ctx, _ptr(buf), buf.size, 1 if checked else 0, C.byref(pf)),
+               worker.ctx)
+        mk = lambda h: Bases(worker, C.c_void_p(h))
+        out = Parameters(worker, mk(pf.p.h), mk(pf.p.l), mk(pf.p.a), mk(pf.p.b_g1), mk(pf.p.b_g2),
+                         bytes(pf.p.alpha_g1), bytes(pf.p.beta_g1), bytes(pf.p.beta_g2), bytes(pf.p.delta_g1),
+                         bytes(pf.p.delta_g2))
+        out.gamma_g2 = bytes(pf.gamma_g2)
+        out.ic = mk(pf.ic)
+        return out
+
+    def write(self):
+        """Parameters::write (groth16/mod.rs:261-290)"""
+        pf = _lib.ParametersFile()
+        pf.p = self._struct()
+        C.memmove(pf.gamma_g2, self.gamma_g2, 192)
+        pf.ic = self.ic.handle
+        n = C.c_size_t()
+        self.worker._lib.bmpc_params_write(self.worker.ctx, C.byref(pf), None, 0, C.byref(n))
+        out = np.empty(n.value, dtype=np.uint8)
+        _raise(self.worker._lib.bmpc_params_write(self.worker.ctx, C.byref(pf), _ptr(out), n.value, C.byref(n)),
+               self.worker.ctx)
+        return out.tobytes()
+
+    def free(self):
+        for b in (self.h, self.l, self.a, self.b_g1, self.b_g2, getattr(self, "ic", None)):
+            if b is not None:
+                b.free()
 
     def _struct(self):
         p = _lib.Params()

@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbellman_b200.so")
 
-OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_LENGTH_MISMATCH, ERR_CUDA, ERR_INVALID = range(7)
+(OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_LENGTH_MISMATCH, ERR_CUDA, ERR_INVALID,
+ ERR_INVALID_DATA) = range(8)
 G1, G2 = 1, 2
 FORM_UNCOMPRESSED_BE, FORM_MONT_XY = 0, 1
 FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
@@ -30,6 +31,7 @@ EXPORTS = [
     "bmpc_domain_mul_assign", "bmpc_domain_sub_assign", "bmpc_ntt_dev", "bmpc_ntt",
     "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
     "bmpc_create_proof", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
+    "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
 ]
 
 
@@ -48,6 +50,11 @@ class Assignment(C.Structure):
                 ("aux_assignment", C.c_void_p), ("num_aux", C.c_size_t),
                 ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p),
                 ("b_aux_density", C.c_void_p)]
+
+
+class ParametersFile(C.Structure):
+    """bmpc_parameters"""
+    _fields_ = [("p", Params), ("gamma_g2", C.c_uint8 * 192), ("ic", C.c_void_p)]
 
 
 _lib = None
@@ -107,6 +114,9 @@ def load():
         "bmpc_create_proof": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), vp, vp, vp]),
         "bmpc_batch_scalar_mul": (i32, [vp, vp, vp, i32, C.POINTER(vp)]),
         "bmpc_fixed_base_mul": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),
+        "bmpc_params_read": (i32, [vp, vp, sz, i32, C.POINTER(ParametersFile)]),
+        "bmpc_params_write": (i32, [vp, C.POINTER(ParametersFile), vp, sz, C.POINTER(sz)]),
+        "bmpc_params_free": (None, [vp, C.POINTER(ParametersFile)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

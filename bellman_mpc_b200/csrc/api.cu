@@ -719,6 +719,144 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
 #undef RCP
 }
 
+// ------------------------------------------------------------- Parameters wire format
+namespace {
+
+// Decode + validate `count` points starting at data[pos]; fewer may be available (short blob).
+// Returns BMPC_OK, BMPC_ERR_INVALID_DATA (ctx->err set) or BMPC_ERR_UNEXPECTED_EOF, in the order
+// the reference's sequential reader would hit them.
+int read_section(bmpc_ctx* ctx, int group, const uint8_t* data, size_t len, size_t* pos, size_t count,
+                 int checked, int reject_identity, bmpc_bases** out, cudaStream_t st) {
+    const size_t pb = group == BMPC_G1 ? 96 : 192;
+    size_t avail = (len - *pos) / pb;
+    size_t n = count < avail ? count : avail;
+    bmpc_bases* b = new bmpc_bases();
+    b->group = group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    uint32_t* d_err = reinterpret_cast<uint32_t*>(ctx->d_stage + 1536);
+    uint32_t h_err = 0xffffffffu;
+    if (n) {
+        uint8_t* d_raw;
+        CK(cudaMalloc(&d_raw, n * pb));
+        CK(cudaMemcpyAsync(d_raw, data + *pos, n * pb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_err, &h_err, 4, cudaMemcpyHostToDevice, st));
+        int rc = group == BMPC_G1
+                     ? GroupOps<Fp>::validate_decode(ctx, d_raw, pb, n, checked, reject_identity, b->d_points, d_err, st)
+                     : GroupOps<Fp2>::validate_decode(ctx, d_raw, pb, n, checked, reject_identity, b->d_points, d_err, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaFree(d_raw));
+    }
+    *pos += n * pb;
+    if (h_err != 0xffffffffu) {
+        ctx->err = (h_err & 3u) == 2u ? "point at infinity" : (group == BMPC_G1 ? "invalid G1" : "invalid G2");
+        bmpc_bases_free(ctx, b);
+        return BMPC_ERR_INVALID_DATA;
+    }
+    if (n < count) {
+        bmpc_bases_free(ctx, b);
+        return BMPC_ERR_UNEXPECTED_EOF;
+    }
+    size_t nw = (n + 31) / 32 + 1;
+    CK(cudaMalloc(&b->d_inf, nw * 4));
+    CK(cudaMemsetAsync(b->d_inf, 0, nw * 4, st));
+    int rc = group == BMPC_G1 ? GroupOps<Fp>::inf_bitmap(ctx, b->d_points, n, b->d_inf, st)
+                              : GroupOps<Fp2>::inf_bitmap(ctx, b->d_points, n, b->d_inf, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    *out = b;
+    return BMPC_OK;
+}
+
+int read_u32_be(const uint8_t* data, size_t len, size_t* pos, size_t* out) {
+    if (*pos + 4 > len) return BMPC_ERR_UNEXPECTED_EOF;
+    const uint8_t* p = data + *pos;
+    *out = ((size_t)p[0] << 24) | ((size_t)p[1] << 16) | ((size_t)p[2] << 8) | p[3];
+    *pos += 4;
+    return BMPC_OK;
+}
+
+}  // namespace
+
+void bmpc_params_free(bmpc_ctx* ctx, bmpc_parameters* p) {
+    if (!p) return;
+    const bmpc_bases** hs[5] = {&p->p.h, &p->p.l, &p->p.a, &p->p.b_g1, &p->p.b_g2};
+    for (auto h : hs) {
+        if (*h) bmpc_bases_free(ctx, const_cast<bmpc_bases*>(*h));
+        *h = nullptr;
+    }
+    if (p->ic) bmpc_bases_free(ctx, p->ic);
+    p->ic = nullptr;
+}
+
+int bmpc_params_read(bmpc_ctx* ctx, const uint8_t* data, size_t len, int checked, bmpc_parameters* out) {
+    if (!ctx || !data || !out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    memset(out, 0, sizeof(*out));
+    size_t pos = 0;
+    // VerifyingKey::read (mod.rs:161-221): six points, always checked, identity allowed
+    struct { int group; uint8_t* dst; } vk[6] = {
+        {BMPC_G1, out->p.alpha_g1}, {BMPC_G1, out->p.beta_g1}, {BMPC_G2, out->p.beta_g2},
+        {BMPC_G2, out->gamma_g2},   {BMPC_G1, out->p.delta_g1}, {BMPC_G2, out->p.delta_g2}};
+    int rc = BMPC_OK;
+    for (int k = 0; k < 6 && rc == BMPC_OK; k++) {
+        size_t pb = vk[k].group == BMPC_G1 ? 96 : 192, before = pos;
+        bmpc_bases* tmp = nullptr;
+        rc = read_section(ctx, vk[k].group, data, len, &pos, 1, 1, 0, &tmp, st);
+        if (rc == BMPC_OK) {
+            memcpy(vk[k].dst, data + before, pb);
+            bmpc_bases_free(ctx, tmp);
+        }
+    }
+    size_t n = 0;
+    if (rc == BMPC_OK) rc = read_u32_be(data, len, &pos, &n);
+    if (rc == BMPC_OK) rc = read_section(ctx, BMPC_G1, data, len, &pos, n, 1, 1, &out->ic, st);   // ic: checked, no identity
+    // Parameters::read (mod.rs:292-400): h, l, a, b_g1 (G1), b_g2 (G2); identity rejected
+    struct { int group; const bmpc_bases** dst; } q[5] = {
+        {BMPC_G1, &out->p.h}, {BMPC_G1, &out->p.l}, {BMPC_G1, &out->p.a}, {BMPC_G1, &out->p.b_g1}, {BMPC_G2, &out->p.b_g2}};
+    for (int k = 0; k < 5 && rc == BMPC_OK; k++) {
+        rc = read_u32_be(data, len, &pos, &n);
+        bmpc_bases* b = nullptr;
+        if (rc == BMPC_OK) rc = read_section(ctx, q[k].group, data, len, &pos, n, checked, 1, &b, st);
+        if (rc == BMPC_OK) *q[k].dst = b;
+    }
+    if (rc != BMPC_OK) {
+        std::string keep = ctx->err;
+        bmpc_params_free(ctx, out);
+        ctx->err = keep;
+    }
+    return rc;
+}
+
+int bmpc_params_write(bmpc_ctx* ctx, const bmpc_parameters* in, uint8_t* out, size_t cap, size_t* written) {
+    if (!ctx || !in || !written || !in->ic || !in->p.h || !in->p.l || !in->p.a || !in->p.b_g1 || !in->p.b_g2)
+        return BMPC_ERR_INVALID;
+    const bmpc_bases* q[6] = {in->ic, in->p.h, in->p.l, in->p.a, in->p.b_g1, in->p.b_g2};
+    size_t need = 864;
+    for (auto b : q) need += 4 + b->n * (b->group == BMPC_G1 ? 96 : 192);
+    *written = need;
+    if (!out || cap < need) return BMPC_ERR_INVALID;
+    uint8_t* p = out;
+    memcpy(p, in->p.alpha_g1, 96); p += 96;
+    memcpy(p, in->p.beta_g1, 96); p += 96;
+    memcpy(p, in->p.beta_g2, 192); p += 192;
+    memcpy(p, in->gamma_g2, 192); p += 192;
+    memcpy(p, in->p.delta_g1, 96); p += 96;
+    memcpy(p, in->p.delta_g2, 192); p += 192;
+    for (auto b : q) {
+        p[0] = (uint8_t)(b->n >> 24); p[1] = (uint8_t)(b->n >> 16); p[2] = (uint8_t)(b->n >> 8); p[3] = (uint8_t)b->n;
+        p += 4;
+        int rc = bmpc_bases_read(ctx, b, 0, b->n, p);
+        if (rc) return rc;
+        p += b->n * (b->group == BMPC_G1 ? 96 : 192);
+    }
+    return BMPC_OK;
+}
+
 // -------------------------------------------------------------- batch scalar multiply
 int bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* scalars, int per_element,
                           bmpc_bases** out) {

@@ -92,6 +92,15 @@ int GroupOps<F>::decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size
 }
 
 template <class F>
+int GroupOps<F>::validate_decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size_t n, int checked,
+                                 int reject_identity, void* d_points, uint32_t* d_err, cudaStream_t st) {
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, validate_decode_kernel<F>, (uint32_t)((n + 63) / 64), 64, 0, st, d_raw, stride, n, checked,
+           reject_identity, reinterpret_cast<Affine<F>*>(d_points), d_err);
+    return BMPC_OK;
+}
+
+template <class F>
 int GroupOps<F>::encode(bmpc_ctx* ctx, const void* d_points, size_t n, uint8_t* d_out, cudaStream_t st) {
     if (!n) return BMPC_OK;
     LAUNCH(ctx, encode_uncompressed_kernel<F>, (uint32_t)((n + 127) / 128), 128, 0, st,

@@ -354,6 +354,74 @@ __global__ void decode_uncompressed_kernel(const uint8_t* in, size_t stride, siz
     }
     store_struct(out + i, a);
 }
+// ---- validating decode (Parameters::read / VerifyingKey::read, groth16/mod.rs:161-221,292-400)
+// G1Affine::from_uncompressed{,_unchecked} of bls12_381 0.6.0: flags, canonical coordinates,
+// and (checked) on-curve + prime-order subgroup.  err <- min over failing points of
+// index * 4 + kind, kind 1 = "invalid G1/G2", 2 = "point at infinity" (identity where rejected).
+__device__ __forceinline__ bool fp_be_canonical(const uint8_t* in, uint8_t mask0) {
+    // big-endian bytes < p ?
+    bool less = false, decided = false;
+    for (int j = 0; j < 12; j++) {
+        uint32_t b0 = in[4 * j], b1 = in[4 * j + 1], b2 = in[4 * j + 2], b3 = in[4 * j + 3];
+        if (j == 0) b0 &= mask0;
+        uint32_t w = (b0 << 24) | (b1 << 16) | (b2 << 8) | b3;
+        uint32_t m = FpParams::mod(11 - j);
+        if (!decided && w != m) { less = w < m; decided = true; }
+    }
+    return decided && less;
+}
+__device__ __forceinline__ bool coord_canonical(const uint8_t* in, uint8_t mask0, const Fp&) {
+    return fp_be_canonical(in, mask0);
+}
+__device__ __forceinline__ bool coord_canonical(const uint8_t* in, uint8_t mask0, const Fp2&) {
+    return fp_be_canonical(in, mask0) && fp_be_canonical(in + 48, 0xff);
+}
+__device__ __forceinline__ Fp curve_b(const Fp&) {            // y^2 = x^3 + 4
+    Fp one = Fp::one(), two = one + one;
+    return two + two;
+}
+__device__ __forceinline__ Fp2 curve_b(const Fp2&) {          // y^2 = x^3 + 4 (1 + u)
+    Fp four = curve_b(Fp::zero());
+    return Fp2{four, four};
+}
+template <class F>
+__global__ void __launch_bounds__(64)
+validate_decode_kernel(const uint8_t* in, size_t stride, size_t n, int checked, int reject_identity,
+                       Affine<F>* out, uint32_t* err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in + i * stride;
+    const int CB = sizeof(F);
+    uint32_t kind = 0;
+    Affine<F> a = Affine<F>::identity();
+    const uint32_t f = p[0];
+    if (!coord_canonical(p, 0x1f, a.x) || !coord_canonical(p + CB, 0xff, a.y) || (f & 0x80) || (f & 0x20)) {
+        kind = 1;
+    } else {
+        get_coord_be(p, 0x1f, a.x);
+        get_coord_be(p + CB, 0xff, a.y);
+        bool zero = a.x.is_zero() && a.y.is_zero();
+        if (f & 0x40) {
+            if (!zero) kind = 1;
+            else if (reject_identity) kind = 2;
+        } else if (zero) {
+            kind = 1;   // (0,0) without the infinity flag: not a curve point (and our identity sentinel)
+        } else if (checked) {
+            F lhs = F::mul_cold(a.y, a.y);
+            F rhs = F::mul_cold(F::mul_cold(a.x, a.x), a.x) + curve_b(a.x);
+            if (lhs != rhs) kind = 1;
+            else {
+                uint32_t r[8];
+                for (int j = 0; j < 8; j++) r[j] = FrParams::mod(j);
+                XYZZ<F> t = XYZZ<F>::from_affine(a).mul(r, 8);     // [r] P == O  <=>  torsion free
+                if (!t.is_identity()) kind = 1;
+            }
+        }
+    }
+    if (kind) atomicMin(err, (uint32_t)(i * 4 + kind));
+    store_struct(out + i, kind ? Affine<F>::identity() : a);
+}
+
 template <class F>
 __global__ void encode_uncompressed_kernel(const Affine<F>* in, size_t n, uint8_t* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

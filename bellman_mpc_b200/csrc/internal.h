@@ -242,6 +242,9 @@ struct GroupOps {
     static int decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size_t n, void* d_points,
                       cudaStream_t st);
     static int encode(bmpc_ctx* ctx, const void* d_points, size_t n, uint8_t* d_out, cudaStream_t st);
+    // validating decode; *d_err must hold 0xffffffff on entry (atomicMin of index*4+kind)
+    static int validate_decode(bmpc_ctx* ctx, const uint8_t* d_raw, size_t stride, size_t n, int checked,
+                               int reject_identity, void* d_points, uint32_t* d_err, cudaStream_t st);
     static int inf_bitmap(bmpc_ctx* ctx, const void* d_points, size_t n, uint32_t* d_bitmap, cudaStream_t st);
     static int batch_mul(bmpc_ctx* ctx, const void* d_in, const uint32_t* d_scalars, int per_element,
                          size_t n, void* d_out, cudaStream_t st);

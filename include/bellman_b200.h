@@ -49,7 +49,8 @@ typedef enum {
     BMPC_ERR_DEGREE_TOO_LARGE = 3,      /* SynthesisError::PolynomialDegreeTooLarge        */
     BMPC_ERR_LENGTH_MISMATCH = 4,       /* the reference's assert!/assert_eq! panics       */
     BMPC_ERR_CUDA = 5,                  /* -> SynthesisError::IoError                      */
-    BMPC_ERR_INVALID = 6                /* malformed argument / encoding                   */
+    BMPC_ERR_INVALID = 6,               /* malformed argument                              */
+    BMPC_ERR_INVALID_DATA = 7           /* io::ErrorKind::InvalidData ("invalid G1", "point at infinity") */
 } bmpc_status;
 
 enum { BMPC_G1 = 1, BMPC_G2 = 2 };
@@ -203,6 +204,23 @@ typedef struct {
  * (Proof::write, src/groth16/mod.rs:42-48). */
 int  bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assignment* asg,
                        const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
+/* ---- Parameters / VerifyingKey wire format  (src/groth16/mod.rs:146-221,261-400) ------------- */
+typedef struct {
+    bmpc_params p;            /* query vectors resident in HBM + the vk points the prover uses    */
+    uint8_t gamma_g2[192];    /* the rest of the VerifyingKey                                     */
+    bmpc_bases* ic;
+} bmpc_parameters;
+/* Parameters::read(reader, checked): parses the blob, decodes and validates every point on the
+ * device (flags, canonical coordinates; vk and ic always, the query vectors when `checked`: on the
+ * curve and in the prime-order subgroup; identity rejected in ic and the query vectors), leaves
+ * the vectors resident.  Errors in stream order like the reference: BMPC_ERR_INVALID_DATA
+ * (bmpc_last_error = "invalid G1" | "invalid G2" | "point at infinity") or
+ * BMPC_ERR_UNEXPECTED_EOF for a short blob. */
+int  bmpc_params_read(bmpc_ctx* ctx, const uint8_t* data, size_t len, int checked, bmpc_parameters* out);
+/* Parameters::write: *written <- size; BMPC_ERR_INVALID with *written set if cap is too small */
+int  bmpc_params_write(bmpc_ctx* ctx, const bmpc_parameters* in, uint8_t* out, size_t cap, size_t* written);
+void bmpc_params_free(bmpc_ctx* ctx, bmpc_parameters* p);
 
 /* ---- batch scalar multiplication  (src/groth16/mpc.rs:647-706 make_new_paramter /
  *      make_new_tau_paramter; also fixed-base CRS synthesis, generator.rs:372-397,492-512) -- */
