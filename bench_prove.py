@@ -94,6 +94,8 @@ class Workload:
         self.crs_setup_s = time.perf_counter() - t0
         self.params = bm.Parameters(w, self.h, self.l, self.qa, self.qb1, self.qb2, vk1[:96], vk1[96:192],
                                     vk2[:192], vk1[192:288], vk2[192:384])
+        self.params.gamma_g2 = vk2[:192]                       # gamma = beta in this synthetic vk
+        self.params.ic = fb(w, bm.G1, G1_GEN, rand_limbs(ni, seed + 24))
         self.assignment = bm.ProvingAssignment(self.a, self.b, self.c, self.inputs, self.aux, *self.dens)
         self.r = bm.fr_to_mont([R_])[0]
         self.s = bm.fr_to_mont([S_])[0]
@@ -198,5 +200,22 @@ def prove_bench(w, log_m, steps, no_cpu_baseline=False, cpu_sample_log=16, preco
         small.prove()
         res["cpu_baseline"]["gpu_seconds_same_sample"] = time.perf_counter() - t0
         small.free()
+    # Parameters::read ingestion on a 2^18-constraint CRS: write, then read back
+    try:
+        pw = Workload(w, 18)
+        blob = pw.params.write()
+        io = {"constraints": 1 << 18, "blob_bytes": len(blob)}
+        for checked in (False, True):
+            t0 = time.perf_counter()
+            back = bm.Parameters.read(w, blob, checked)
+            dt = time.perf_counter() - t0
+            ok = back.write() == blob
+            io["checked" if checked else "unchecked"] = {"seconds": dt, "gb_per_s": len(blob) / dt / 1e9,
+                                                         "roundtrip_identical": bool(ok)}
+            back.free()
+        res["params_read"] = io
+        pw.free()
+    except Exception as e:
+        res["params_read"] = {"error": repr(e)}
     wl.free()
     return res

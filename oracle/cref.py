@@ -14,15 +14,33 @@ _PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
 
+def _cpu_signature():
+    """The library is compiled with -march=native (the timed CPU baseline should be as fast as
+    the host allows), so a copy built on another machine is rebuilt before use."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build():
-    subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-B", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    with open(os.path.join(_HERE, "_build", "cpu.sig"), "w") as f:
+        f.write(_cpu_signature())
 
 
 def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_PATH):
+    sig_path = os.path.join(_HERE, "_build", "cpu.sig")
+    sig = open(sig_path).read() if os.path.exists(sig_path) else ""
+    if not os.path.exists(_PATH) or sig != _cpu_signature():
         build()
     lib = C.CDLL(_PATH)
     vp, sz, i32, u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
