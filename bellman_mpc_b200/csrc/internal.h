@@ -15,7 +15,8 @@
 
 namespace bmpc {
 
-constexpr uint32_t SMALL_LOG = 10;  // largest in-block NTT radix 2^10
+constexpr uint32_t SMALL_LOG = 12;   // largest in-block NTT radix 2^12 (128 KB of shared memory)
+constexpr uint32_t DIRECT_TABLE_MAX_LOG = 24;  // fully expanded power tables up to this domain size
 
 enum TableKind {
     K_TW_FWD = 0, K_TW_INV, K_G, K_G_MINV, K_GINV_MINV, K_GINV_MINV_ZINV_CANON, K_COUNT
@@ -24,6 +25,7 @@ enum TableKind {
 struct DevTable {
     Fr* hi = nullptr;
     Fr* lo = nullptr;
+    Fr* direct = nullptr;
     uint32_t lo_bits = 0, hi_n = 0;
     bool ready = false;
 };

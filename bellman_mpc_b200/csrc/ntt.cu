@@ -1,6 +1,7 @@
 // Host side of the EvaluationDomain transforms: per-size constant/twiddle tables, pass
 // planning, the fused H-polynomial pipeline.  Kernels are in ntt.cuh.
 // Reference: src/domain.rs:47-189,261-372; src/groth16/prover.rs:210-231.
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -45,7 +46,7 @@ static int get_table(bmpc_ctx* ctx, DomainTables* dt, uint32_t logm, TableKind k
             case K_GINV_MINV_ZINV_CANON: base_idx = 4; fold_idx = 6; canon = 1; break;
             default: return BMPC_ERR_INVALID;
         }
-        t.lo_bits = logm <= SMALL_LOG ? logm : (logm + 1) / 2;
+        t.lo_bits = logm <= 10 ? logm : (logm + 1) / 2;
         t.hi_n = 1u << (logm - t.lo_bits);
         uint32_t lo_n = 1u << t.lo_bits;
         CK(cudaMalloc(&t.lo, (size_t)lo_n * sizeof(Fr)));
@@ -55,12 +56,21 @@ static int get_table(bmpc_ctx* ctx, DomainTables* dt, uint32_t logm, TableKind k
                (uint64_t)1, lo_n, canon, t.lo);
         LAUNCH(ctx, pow_table_kernel, (t.hi_n + 127) / 128, 128, 0, st, (const Fr*)(dt->d_consts + base_idx),
                (const Fr*)nullptr, (uint64_t)1 << t.lo_bits, t.hi_n, 0, t.hi);
+        // 2-level tables cost one extra product per lookup; up to 2^24 the full table is expanded
+        // once (32 B per coefficient in HBM, read once per pass that uses it)
+        if (t.hi_n > 1 && logm <= DIRECT_TABLE_MAX_LOG && !(getenv("BMPC_NTT_NO_DIRECT") && atoi(getenv("BMPC_NTT_NO_DIRECT")))) {
+            uint32_t cnt = 1u << logm;
+            CK(cudaMalloc(&t.direct, (size_t)cnt * sizeof(Fr)));
+            PowTable two{t.hi, t.lo, t.lo_bits, t.hi_n, nullptr};
+            LAUNCH(ctx, pow_expand_kernel, (cnt + 255) / 256, 256, 0, st, two, cnt, t.direct);
+        }
         t.ready = true;
     }
     out->hi = t.hi;
     out->lo = t.lo;
     out->lo_bits = t.lo_bits;
     out->hi_n = t.hi_n;
+    out->direct = t.direct;
     return BMPC_OK;
 }
 
@@ -70,6 +80,7 @@ void ntt_free_tables(bmpc_ctx* ctx) {
         for (int k = 0; k < K_COUNT; k++) {
             if (kv.second.t[k].hi) cudaFree(kv.second.t[k].hi);
             if (kv.second.t[k].lo) cudaFree(kv.second.t[k].lo);
+            if (kv.second.t[k].direct) cudaFree(kv.second.t[k].direct);
         }
     }
     ctx->domains.clear();
@@ -117,6 +128,9 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
     }
     rc = get_table(ctx, dt, logm, inverse ? K_TW_INV : K_TW_FWD, st, &A.tw);
     if (rc) return rc;
+    // 2^8 per pass with 4 sub-transforms per block measured fastest on B200 (2^24: 4.99 ms vs 5.58 ms
+    // for two 2^12 passes, whose single-sub-transform layout has shared-memory bank conflicts in the
+    // late stages); larger radices stay available through the tuning knob.
     uint32_t maxdeg = ctx->tune_maxdeg ? (uint32_t)ctx->tune_maxdeg : 8u;
     if (maxdeg > SMALL_LOG) maxdeg = SMALL_LOG;
     if (maxdeg < 1) maxdeg = 1;
@@ -130,9 +144,9 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
         else if (j == npass - 1) dst = data;
         else dst = (j & 1) ? tmp2 : tmp1;
         uint32_t tlog = logm - deg;
-        uint32_t tile_log = 2;
+        // T consecutive i per block while the tile stays within 32 KB; big radices run T = 1
+        uint32_t tile_log = deg >= 10 ? 0 : (10 - deg > 2 ? 2 : 10 - deg);
         if (tile_log > tlog) tile_log = tlog;
-        if (tile_log > 10 - deg) tile_log = 10 - deg;
         A.in = src; A.out = dst;
         A.deg = deg; A.plog = plog; A.tile_log = tile_log;
         A.pre_mode = (j == 0) ? sc.pre_mode : SCALE_NONE;
@@ -141,8 +155,11 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
         A.post = post;
         if (A.post_mode == SCALE_CONST) A.post_const = dt->h_consts[sc.post_const_idx];
         uint32_t threads = 1u << (tile_log + deg - 1);
+        if (threads > 1024) threads = 1024;
         uint32_t blocks = 1u << (tlog - tile_log);
         size_t smem = ((size_t)1 << (tile_log + deg)) * sizeof(Fr);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             ProfScope ps(ctx, BMPC_PROF_NTT_PASS, st);
             LAUNCH(ctx, ntt_pass_kernel, blocks, threads, smem, st, A);

@@ -23,7 +23,8 @@ struct PowTable {
     const Fr* hi;
     const Fr* lo;
     uint32_t lo_bits;
-    uint32_t hi_n;  // entries in hi; 1 => lo alone covers the range
+    uint32_t hi_n;      // entries in hi; 1 => lo alone covers the range
+    const Fr* direct;   // optional: all 2^logm powers expanded (one load, no product); may be NULL
 };
 
 enum { SCALE_NONE = 0, SCALE_CONST = 1, SCALE_POW = 2 };
@@ -62,6 +63,7 @@ __device__ __forceinline__ void store_fr(Fr* p, const Fr& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 __device__ __forceinline__ Fr pow_lookup(const PowTable& t, uint32_t e) {
+    if (t.direct) return ldg_fr(t.direct + e);
     Fr lo = ldg_fr(t.lo + (e & ((1u << t.lo_bits) - 1u)));
     if (t.hi_n == 1) return lo;
     return lo * ldg_fr(t.hi + (e >> t.lo_bits));
@@ -72,31 +74,29 @@ __device__ __forceinline__ Fr pow_lookup(const PowTable& t, uint32_t e) {
 //     v[s]  = in[i + s t] * omega_n^{(t/p) k s}                 s in [0, R)
 //     V     = DFT_R(v)            (DIF stages in shared memory, read out bit-reversed)
 //     out[(i - k) R + k + s' p] = V[s']
-// Block = T consecutive i  x  R/2 butterflies; shared layout u[s][i_local].
-__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
+// Block = T consecutive i, R = 2^deg up to 2^12 (128 KB of shared memory: a 2^24 transform is two
+// passes); threads loop over the T R / 2 butterflies of a stage.  Shared layout u[s][i_local].
+__global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassArgs A) {
     extern __shared__ uint4 ntt_smem[];
     Fr* u = reinterpret_cast<Fr*>(ntt_smem);
     const uint32_t deg = A.deg, R = 1u << deg, T = 1u << A.tile_log;
     const uint32_t tlog = A.logn - deg;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t il = tid & (T - 1u);
-    const uint32_t b = tid >> A.tile_log;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t tile_base = blockIdx.x << A.tile_log;
-    const uint32_t i = tile_base + il;
     const uint32_t pmask = (1u << A.plog) - 1u;
-    const uint32_t k = i & pmask;
+    const uint32_t total = T << deg;              // elements held by the block
 
-#pragma unroll 1
-    for (uint32_t h = 0; h < 2; h++) {
-        uint32_t s = b + h * (R >> 1);
+    for (uint32_t e = tid; e < total; e += nthr) {
+        uint32_t il = e & (T - 1u), s = e >> A.tile_log;
+        uint32_t i = tile_base + il;
         uint32_t src = i + (s << tlog);
         Fr v = load_fr(A.in + src);
         if (A.pre_mode == SCALE_POW) v = v * pow_lookup(A.pre, src);
         if (A.plog != 0) {
-            uint32_t e = (k * s) << (tlog - A.plog);
-            if (e != 0) v = v * pow_lookup(A.tw, e);
+            uint32_t ex = ((i & pmask) * s) << (tlog - A.plog);
+            if (ex != 0) v = v * pow_lookup(A.tw, ex);
         }
-        u[s * T + il] = v;
+        u[e] = v;                                  // u[s * T + il]
     }
     __syncthreads();
 
@@ -104,29 +104,29 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
 #pragma unroll 1
     for (uint32_t rnd = 0; rnd < deg; rnd++) {
         uint32_t half = R >> (rnd + 1);
-        uint32_t di = b & (half - 1u);
-        uint32_t i0 = ((b - di) << 1) + di;
-        uint32_t i1 = i0 + half;
-        Fr x0 = u[i0 * T + il];
-        Fr x1 = u[i1 * T + il];
-        u[i0 * T + il] = x0 + x1;
-        Fr d = x0 - x1;
-        if (di != 0) d = d * ldg_fr(A.tw_small + ((di << rnd) << sshift));
-        u[i1 * T + il] = d;
+        for (uint32_t bb = tid; bb < (total >> 1); bb += nthr) {
+            uint32_t il = bb & (T - 1u), b = bb >> A.tile_log;
+            uint32_t di = b & (half - 1u);
+            uint32_t i0 = ((b - di) << 1) + di;
+            uint32_t i1 = i0 + half;
+            Fr x0 = u[i0 * T + il];
+            Fr x1 = u[i1 * T + il];
+            u[i0 * T + il] = x0 + x1;
+            Fr d = x0 - x1;
+            if (di != 0) d = d * ldg_fr(A.tw_small + ((di << rnd) << sshift));
+            u[i1 * T + il] = d;
+        }
         __syncthreads();
     }
 
-    const uint32_t half_threads = T << (deg - 1);  // == blockDim.x
-#pragma unroll 1
-    for (uint32_t h = 0; h < 2; h++) {
+    for (uint32_t e = tid; e < total; e += nthr) {
         uint32_t sp, il2;
         if (A.plog >= A.tile_log) {  // consecutive threads -> consecutive k: contiguous stores
-            il2 = il;
-            sp = b + h * (R >> 1);
+            il2 = e & (T - 1u);
+            sp = e >> A.tile_log;
         } else {                      // first pass (p < T): consecutive threads -> consecutive s'
-            uint32_t o = tid + h * half_threads;
-            sp = o & (R - 1u);
-            il2 = o >> deg;
+            sp = e & (R - 1u);
+            il2 = e >> deg;
         }
         uint32_t i2 = tile_base + il2;
         uint32_t k2 = i2 & pmask;
@@ -136,6 +136,14 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
         else if (A.post_mode == SCALE_POW) v = v * pow_lookup(A.post, dst);
         store_fr(A.out + dst, v);
     }
+}
+
+// direct[e] = hi[e >> lo_bits] * lo[e & mask]  (expands a two-level table once)
+__global__ void pow_expand_kernel(PowTable t, uint32_t count, Fr* out) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    Fr lo = ldg_fr(t.lo + (e & ((1u << t.lo_bits) - 1u)));
+    store_fr(out + e, t.hi_n == 1 ? lo : lo * ldg_fr(t.hi + (e >> t.lo_bits)));
 }
 
 // n == 1 transform: only the scalings apply.

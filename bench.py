@@ -191,12 +191,21 @@ def run_ours(args):
 
     n_total = 1 << args.log_n
     n = n_total // world
+    grp = bm.G2 if args.group == "g2" else bm.G1
+    pt_bytes = 96 if grp == bm.G1 else 192
+    bytes_per_point = pt_bytes + 32                       # affine base + scalar
+    mul_per_add = 10 * (1 if grp == bm.G1 else 3)         # 8M+2S; an Fp2 product = 3 Fp products
+    g2_gen = bytes.fromhex(
+        "13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+        "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"
+        "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be"
+        "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801")
     curves_gen = bytes.fromhex(
         "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
         "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1")
     ks = rand_limbs(n, 2 + 7919 * rank)
     t_setup = time.perf_counter()
-    bases = bm.Bases.fixed_base_mul(w, bm.G1, curves_gen, ks)          # resident CRS slice, k_i * G
+    bases = bm.Bases.fixed_base_mul(w, grp, curves_gen if grp == bm.G1 else g2_gen, ks)   # resident CRS slice, k_i * G
     if not args.no_precompute:
         bases.precompute()                                               # window tables in HBM (setup)
     scalars_h = torch.from_numpy(rand_limbs(n, 1 + 7919 * rank).view(np.int64)).pin_memory()
@@ -204,10 +213,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
-    pbytes = int(lib.bmpc_partial_bytes(bm.G1))
+    pbytes = int(lib.bmpc_partial_bytes(grp))
     partial = torch.zeros(pbytes, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(world * pbytes, dtype=torch.uint8, device=dev)
-    out = np.zeros(96, dtype=np.uint8)
+    out = np.zeros(pt_bytes, dtype=np.uint8)
     import ctypes as C
     optr = out.ctypes.data_as(C.c_void_p)
 
@@ -218,7 +227,7 @@ def run_ours(args):
             st = lib.bmpc_multiexp_partial_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, partial.data_ptr(), stream)
             assert st == 0, st
             dist.all_gather_into_tensor(gathered, partial)
-            st = lib.bmpc_sum_partials(w.ctx, bm.G1, gathered.data_ptr(), world, optr, stream)
+            st = lib.bmpc_sum_partials(w.ctx, grp, gathered.data_ptr(), world, optr, stream)
         assert st == 0, (st, lib.bmpc_last_error(w.ctx))
 
     def barrier():
@@ -284,13 +293,13 @@ def run_ours(args):
     peaks = measured_peaks()
     acc_ms, acc_cnt = prof["accumulate"]
     roofline = {
-        "kernel": "msm_accumulate_kernel<Fp>", "bound": "hbm",
-        "achieved": G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
+        "kernel": "msm_accumulate_kernel<%s>" % ("Fp" if grp == bm.G1 else "Fp2"), "bound": "hbm",
+        "achieved": bytes_per_point * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
         "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": (G1_MSM_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
-        "traffic": peaks.get("acc_traffic_bytes") if (world == 1 and args.log_n == 24 and not args.no_precompute) else None,
+        "frac": (bytes_per_point * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
+        "traffic": peaks.get("acc_traffic_bytes") if (world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute) else None,
         "traffic_source": "profiles/r01_ncu_kernel_summaries.json (ncu --set full, same command, 1 GPU, 2^24)",
-        "algorithmic_bytes": G1_MSM_BYTES_PER_POINT * n,
+        "algorithmic_bytes": bytes_per_point * n,
         "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
         "kernel_ms": acc_ms, "share_of_step": acc_ms / ms if ms else None,
         "note": "integer-pipe bound, not HBM bound: see roofline_int",
@@ -299,21 +308,22 @@ def run_ours(args):
     cw, ww, hh = C.c_uint32(), C.c_uint32(), C.c_uint32()
     lib.bmpc_msm_geometry(w.ctx, bases.handle, n, C.byref(cw), C.byref(ww), C.byref(hh))
     if peaks.get("mac32_per_s") and acc_ms:
-        executed = 10 * 300 * ww.value * n            # 8M+2S mixed additions actually issued
+        executed = mul_per_add * 300 * ww.value * n   # 8M+2S mixed additions actually issued
         ach = executed / (acc_ms * 1e-3)
         roofline_int = {"kernel": "msm_accumulate_kernel<Fp>", "bound": "int32-mac",
                         "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12, "unit": "TMAC32/s",
                         "frac": ach / peaks["mac32_per_s"],
                         "peak_source": "profiles/r01_imad_peak.json (mad.lo.cc/madc.hi.cc chains, measured)",
-                        "work": f"executed: {ww.value} windows of c={cw.value} bits x 10 Fp mul x 300 MAC32 per point",
-                        "survey_model_frac": G1_MSM_MAC32_PER_POINT * n / (acc_ms * 1e-3) / peaks["mac32_per_s"],
+                        "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp mul x 300 MAC32 per point",
+                        "survey_model_frac": (G1_MSM_MAC32_PER_POINT if grp == bm.G1 else G2_MSM_MAC32_PER_POINT) * n / (acc_ms * 1e-3) / peaks["mac32_per_s"],
                         "survey_model": "48000 MAC32 per point (SURVEY 8d: fixed 16 windows)"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if (grp == bm.G1 and args.log_n == 24) else f"{args.group}_msm_mpts_per_s_2p{args.log_n}",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32-limb Montgomery (Fp 12x32, Fr 8x32)", "data": "synthetic",
-        "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity "
+        "config": {"workload": f"{args.group.upper()} multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity "
                                f"(BASELINE configs[1] shape at the size the metric is quoted on)",
                    "bases": "k_i*G, resident (CRS registered once%s)" % ("" if args.no_precompute else
                             ", window tables 2^(cw)*P_i precomputed at registration"), "points_per_gpu": n,
@@ -329,7 +339,7 @@ def run_ours(args):
     }
 
     # ---- CPU baseline beside it (rank 0, N = 1): oracle on a bounded sample + parity check
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and grp == bm.G1:
         from oracle import cref
         threads = cref.hardware_threads()
         slog = args.ref_sample_log
@@ -346,7 +356,7 @@ def run_ours(args):
         cb.free()
 
     # ---- Groth16 prove @ 2^prove_log_n (N = 1), same run
-    if world == 1 and not args.no_prove:
+    if world == 1 and not args.no_prove and grp == bm.G1:
         try:
             from bench_prove import prove_bench
             line["prove"] = prove_bench(w, args.prove_log_n, max(2, args.steps // 2), args.no_cpu_baseline,
@@ -405,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--group", default="g1", choices=["g1", "g2"])
     ap.add_argument("--ref-sample-log", type=int, default=18)
     ap.add_argument("--prove-log-n", type=int, default=22)
     ap.add_argument("--no-prove", action="store_true")
