@@ -480,6 +480,73 @@ def create_proof(assignment, params, r_mont, s_mont):
     return out.tobytes()
 
 
+class CsrMatrix:
+    """R1CS matrix in CSR form (bmpc_csr): rows of (column, Montgomery coefficient)."""
+
+    def __init__(self, row_ptr, col, coeff_mont):
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        self.col = np.ascontiguousarray(col, dtype=np.uint32)
+        self.coeff = np.ascontiguousarray(coeff_mont, dtype=np.uint64).reshape(-1, 4)
+        assert self.row_ptr[-1] == len(self.col) == self.coeff.shape[0]
+
+    @staticmethod
+    def from_rows(rows):
+        """rows: list of lists of (column, canonical int coefficient)"""
+        row_ptr, col, coeff = [0], [], []
+        for r in rows:
+            for c, v in r:
+                col.append(c)
+                coeff.append(v % FR_MODULUS)
+            row_ptr.append(len(col))
+        return CsrMatrix(row_ptr, col, fr_to_mont(coeff) if coeff else np.zeros((0, 4), dtype=np.uint64))
+
+    @property
+    def num_rows(self):
+        return len(self.row_ptr) - 1
+
+    def _struct(self):
+        s = _lib.Csr()
+        s.row_ptr, s.col, s.coeff = _ptr(self.row_ptr), _ptr(self.col), _ptr(self.coeff)
+        s.num_rows, s.nnz = self.num_rows, len(self.col)
+        return s
+
+
+def r1cs_eval(worker, A, B, C_, input_assignment, aux_assignment):
+    """ProvingAssignment::enforce over the whole system + create_proof's input rows
+    (prover.rs:19-53,100-138,202-204) -> ProvingAssignment ready for create_proof."""
+    as4 = lambda x: np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+    inp, aux = as4(input_assignment), as4(aux_assignment)
+    ni, na = inp.shape[0], aux.shape[0]
+    total = A.num_rows + ni
+    a, b, c = (np.empty((total, 4), dtype=np.uint64) for _ in range(3))
+    da, dbi, dba = (np.zeros(max(1, (n + 63) // 64), dtype=np.uint64) for n in (na, ni, na))
+    sa, sb, sc = A._struct(), B._struct(), C_._struct()
+    _raise(worker._lib.bmpc_r1cs_eval(worker.ctx, C.byref(sa), C.byref(sb), C.byref(sc), ni, na, _ptr(inp), _ptr(aux),
+                                      _ptr(a), _ptr(b), _ptr(c), _ptr(da), _ptr(dbi), _ptr(dba)), worker.ctx)
+    unpack = lambda w, n: DensityTracker.from_bits(np.unpackbits(w.view(np.uint8), bitorder="little")[:n])
+    return ProvingAssignment(a, b, c, inp, aux, unpack(da, na), unpack(dbi, ni), unpack(dba, na))
+
+
+def generate_parameters(worker, At, Bt, Ct, num_inputs, num_aux, num_constraints, g1, g2, alpha, beta, gamma, delta,
+                        tau):
+    """generate_parameters, upstream semantics (generator.rs:241-634).  At/Bt/Ct: transposed R1CS
+    (one row per variable); scalars canonical ints; g1/g2 uncompressed bytes."""
+    pf = _lib.ParametersFile()
+    sa, sb, sc = At._struct(), Bt._struct(), Ct._struct()
+    g1b, g2b = np.frombuffer(bytes(g1), dtype=np.uint8), np.frombuffer(bytes(g2), dtype=np.uint8)
+    ks = [fr_to_mont([k])[0] for k in (alpha, beta, gamma, delta, tau)]
+    _raise(worker._lib.bmpc_generate_parameters(worker.ctx, C.byref(sa), C.byref(sb), C.byref(sc), num_inputs, num_aux,
+                                                num_constraints, _ptr(g1b), _ptr(g2b), *(_ptr(k) for k in ks),
+                                                C.byref(pf)), worker.ctx)
+    mk = lambda h: Bases(worker, C.c_void_p(h))
+    out = Parameters(worker, mk(pf.p.h), mk(pf.p.l), mk(pf.p.a), mk(pf.p.b_g1), mk(pf.p.b_g2),
+                     bytes(pf.p.alpha_g1), bytes(pf.p.beta_g1), bytes(pf.p.beta_g2), bytes(pf.p.delta_g1),
+                     bytes(pf.p.delta_g2))
+    out.gamma_g2 = bytes(pf.gamma_g2)
+    out.ic = mk(pf.ic)
+    return out
+
+
 def create_random_proof(assignment, params, rng=None):
     """prover.rs:158-173: the fork ignores the RNG and uses r = 27134, s = 17146."""
     return create_proof(assignment, params, fr_to_mont([27134])[0], fr_to_mont([17146])[0])

@@ -32,6 +32,7 @@ EXPORTS = [
     "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
     "bmpc_create_proof", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
+    "bmpc_r1cs_eval", "bmpc_generate_parameters",
 ]
 
 
@@ -50,6 +51,12 @@ class Assignment(C.Structure):
                 ("aux_assignment", C.c_void_p), ("num_aux", C.c_size_t),
                 ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p),
                 ("b_aux_density", C.c_void_p)]
+
+
+class Csr(C.Structure):
+    """bmpc_csr"""
+    _fields_ = [("row_ptr", C.c_void_p), ("col", C.c_void_p), ("coeff", C.c_void_p),
+                ("num_rows", C.c_size_t), ("nnz", C.c_size_t)]
 
 
 class ParametersFile(C.Structure):
@@ -117,6 +124,9 @@ def load():
         "bmpc_params_read": (i32, [vp, vp, sz, i32, C.POINTER(ParametersFile)]),
         "bmpc_params_write": (i32, [vp, C.POINTER(ParametersFile), vp, sz, C.POINTER(sz)]),
         "bmpc_params_free": (None, [vp, C.POINTER(ParametersFile)]),
+        "bmpc_r1cs_eval": (i32, [vp, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Csr), sz, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "bmpc_generate_parameters": (i32, [vp, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Csr), sz, sz, sz, vp, vp,
+                                           vp, vp, vp, vp, vp, C.POINTER(ParametersFile)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

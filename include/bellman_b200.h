@@ -222,6 +222,34 @@ int  bmpc_params_read(bmpc_ctx* ctx, const uint8_t* data, size_t len, int checke
 int  bmpc_params_write(bmpc_ctx* ctx, const bmpc_parameters* in, uint8_t* out, size_t cap, size_t* written);
 void bmpc_params_free(bmpc_ctx* ctx, bmpc_parameters* p);
 
+/* ---- constraint-system side -------------------------------------------------- */
+/* R1CS matrix in CSR form.  For bmpc_r1cs_eval: one row per constraint, columns = variables
+ * ([0, num_inputs) inputs with column 0 = ONE, then aux).  For bmpc_generate_parameters: the
+ * TRANSPOSE -- one row per variable listing (coeff, constraint), the KeypairAssembly layout of
+ * generator.rs:44-156.  coeff: Montgomery 4 x u64. */
+typedef struct {
+    const uint32_t* row_ptr;   /* num_rows + 1 */
+    const uint32_t* col;       /* nnz */
+    const uint64_t* coeff;     /* nnz x 4 */
+    size_t num_rows, nnz;
+} bmpc_csr;
+/* ProvingAssignment::enforce for the whole system (prover.rs:19-53,100-138) plus the `x * 0 = 0`
+ * rows create_proof appends per input (:202-204).  Outputs (host): a, b, c of
+ * (A->num_rows + num_inputs) x 4 u64 Montgomery, and the three density maps (bitvec words). */
+int  bmpc_r1cs_eval(bmpc_ctx* ctx, const bmpc_csr* A, const bmpc_csr* B, const bmpc_csr* C, size_t num_inputs,
+                    size_t num_aux, const uint64_t* input_assignment, const uint64_t* aux_assignment,
+                    uint64_t* a_out, uint64_t* b_out, uint64_t* c_out, uint64_t* a_aux_density,
+                    uint64_t* b_input_density, uint64_t* b_aux_density);
+/* generate_parameters with upstream semantics (generator.rs:241-634 minus the fork's MPC
+ * cross-check hooks): num_constraints = user constraints (the input rows are appended here, :273-275);
+ * g1/g2 uncompressed generators; scalars Montgomery.  BMPC_ERR_UNEXPECTED_IDENTITY if gamma or delta
+ * is zero (:330-345); BMPC_ERR_INVALID_DATA ("UnconstrainedVariable", :584-590). */
+int  bmpc_generate_parameters(bmpc_ctx* ctx, const bmpc_csr* At, const bmpc_csr* Bt, const bmpc_csr* Ct,
+                              size_t num_inputs, size_t num_aux, size_t num_constraints, const uint8_t g1[96],
+                              const uint8_t g2[192], const uint64_t alpha[4], const uint64_t beta[4],
+                              const uint64_t gamma[4], const uint64_t delta[4], const uint64_t tau[4],
+                              bmpc_parameters* out);
+
 /* ---- batch scalar multiplication  (src/groth16/mpc.rs:647-706 make_new_paramter /
  *      make_new_tau_paramter; also fixed-base CRS synthesis, generator.rs:372-397,492-512) -- */
 /* out[i] = in[i] * k[i] (per_element = 1) or in[i] * k[0] (per_element = 0); k canonical 4 x u64 */
