@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -93,11 +94,18 @@ namespace bmpc {
         }                                                                             \
     } while (0)
 
+// BMPC_SYNC_CHECK=1 synchronises after every launch so that a fault is reported at its kernel.
+inline bool bmpc_sync_check() {
+    static const bool on = getenv("BMPC_SYNC_CHECK") && atoi(getenv("BMPC_SYNC_CHECK")) != 0;
+    return on;
+}
+
 #define LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                           \
     do {                                                                              \
         kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                           \
         (ctx)->launches++;                                                            \
         cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ == cudaSuccess && bmpc::bmpc_sync_check()) e_ = cudaDeviceSynchronize(); \
         if (e_ != cudaSuccess) {                                                      \
             (ctx)->err = std::string(#kernel) + ": " + cudaGetErrorString(e_);        \
             return BMPC_ERR_CUDA;                                                     \

@@ -308,7 +308,7 @@ int bmpc_generate_parameters(bmpc_ctx* ctx, const bmpc_csr* At, const bmpc_csr* 
     RK(cudaMemcpyAsync(d_raw + 96, g2, 192, cudaMemcpyHostToDevice, st));
     RC(GroupOps<Fp>::decode(ctx, d_raw, 96, 1, d_base1, st));
     RC(GroupOps<Fp2>::decode(ctx, d_raw + 96, 192, 1, d_base2, st));
-    RK(cudaMalloc(&d_pts, (big ? big : 1) * 192));
+    RK(cudaMalloc(&d_pts, (big > 8 ? big : 8) * 192));      // also the 1152-byte vk encode scratch
     RK(cudaMalloc(&d_flags, (nv + 1) * 4)); RK(cudaMalloc(&d_pos, (nv + 2) * 4));
     RK(cudaMalloc(&d_chunks, (nv / 1024 + 4) * 4));
 
@@ -329,6 +329,8 @@ int bmpc_generate_parameters(bmpc_ctx* ctx, const bmpc_csr* At, const bmpc_csr* 
                 if (group == BMPC_G1) compact_kernel<24><<<(uint32_t)((n + 127) / 128), 128, 0, st>>>((const uint32_t*)d_pts, keep_flags, keep_pos, n, (uint32_t*)b->d_points);
                 else compact_kernel<48><<<(uint32_t)((n + 127) / 128), 128, 0, st>>>((const uint32_t*)d_pts, keep_flags, keep_pos, n, (uint32_t*)b->d_points);
                 ctx->launches++;
+                cudaError_t ce = cudaGetLastError();
+                if (ce != cudaSuccess) { ctx->err = std::string("compact_kernel: ") + cudaGetErrorString(ce); bmpc_bases_free(ctx, b); return BMPC_ERR_CUDA; }
             }
         } else if (n) {
             cudaMemcpyAsync(b->d_points, d_pts, n * pb, cudaMemcpyDeviceToDevice, st);
