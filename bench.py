@@ -364,6 +364,15 @@ def run_ours(args):
         except Exception as e:  # keep the headline line even if the secondary workload fails
             line["prove"] = {"error": repr(e)}
 
+    # ---- constraint evaluation + key generation on the device
+    if world == 1 and not args.no_r1cs and grp == bm.G1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "bench"))
+            import r1cs_bench
+            line["r1cs"] = r1cs_bench.run(w, args.r1cs_log_n)
+        except Exception as e:
+            line["r1cs"] = {"error": repr(e)}
+
     # ---- EvaluationDomain sweep (BASELINE config #3): fft on resident coefficients, GB/s vs HBM peak
     if world == 1 and not args.no_ntt:
         ntt = []
@@ -422,6 +431,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-r1cs", action="store_true")
+    ap.add_argument("--r1cs-log-n", type=int, default=18)
     ap.add_argument("--ntt-max-log", type=int, default=26)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
