@@ -30,7 +30,7 @@ EXPORTS = [
     "bmpc_domain_distribute_powers", "bmpc_domain_z", "bmpc_domain_divide_by_z_on_coset",
     "bmpc_domain_mul_assign", "bmpc_domain_sub_assign", "bmpc_ntt_dev", "bmpc_ntt",
     "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
-    "bmpc_create_proof", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
+    "bmpc_create_proof", "bmpc_create_proof_partials", "bmpc_create_proof_finish", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
     "bmpc_r1cs_eval", "bmpc_generate_parameters",
 ]
@@ -51,6 +51,14 @@ class Assignment(C.Structure):
                 ("aux_assignment", C.c_void_p), ("num_aux", C.c_size_t),
                 ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p),
                 ("b_aux_density", C.c_void_p)]
+
+
+PROOF_PARTIAL_BYTES = 1920      # BMPC_PROOF_PARTIAL_BYTES: 6 G1 XYZZ (192 B) + 2 G2 XYZZ (384 B)
+
+
+class ProofShard(C.Structure):
+    """bmpc_proof_shard"""
+    _fields_ = [("base_offset", C.c_size_t * 8), ("h_lo", C.c_size_t), ("h_hi", C.c_size_t)]
 
 
 class Csr(C.Structure):
@@ -119,6 +127,9 @@ def load():
         "bmpc_h_coefficients_dev": (i32, [vp, vp, vp, vp, u32, vp]),
         "bmpc_fr_to_canonical_dev": (i32, [vp, vp, sz, vp]),
         "bmpc_create_proof": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), vp, vp, vp]),
+        "bmpc_create_proof_partials": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), C.POINTER(ProofShard), vp,
+                                             C.POINTER(i32 * 8)]),
+        "bmpc_create_proof_finish": (i32, [vp, C.POINTER(Params), vp, sz, vp, vp, vp]),
         "bmpc_batch_scalar_mul": (i32, [vp, vp, vp, i32, C.POINTER(vp)]),
         "bmpc_fixed_base_mul": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),
         "bmpc_params_read": (i32, [vp, vp, sz, i32, C.POINTER(ParametersFile)]),

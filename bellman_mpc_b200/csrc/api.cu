@@ -44,6 +44,8 @@ int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offs
     uint8_t* d_bytes = ctx->d_stage + 64;
     int mode = d_partial ? 1 : 0;
     MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr);
+    if (bases->group == BMPC_G1) GroupOps<Fp>::plan_affine(ctx, p);
+    else GroupOps<Fp2>::plan_affine(ctx, p);
     size_t curve_bytes = bases->group == BMPC_G1 ? GroupOps<Fp>::curve_bytes(p) : GroupOps<Fp2>::curve_bytes(p);
     rc = ws_reserve(ctx, p.sort_bytes + curve_bytes);
     if (rc) return rc;
@@ -562,9 +564,16 @@ int bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* st
 }
 
 // ----------------------------------------------------------------------- create_proof
-int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
-                      const uint64_t s[4], uint8_t proof_out[192]) {
-    if (!ctx || !P || !S || !r || !s || !proof_out) return BMPC_ERR_INVALID;
+}  // extern "C"
+namespace {
+// Shared body of bmpc_create_proof (shard == NULL: the eight multiexps, then the tail, 192-byte
+// proof) and bmpc_create_proof_partials (one rank's share of the multiexps: `S` is the rank's
+// SLICE of the assignment, shard->base_offset[j] the first base each multiexp consumes inside the
+// rank's slice of the query vector, [h_lo, h_hi) its share of the H coefficients; the XYZZ partial
+// sums go to partials_out, the per-multiexp statuses to statuses_out, no tail).
+int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
+                        const uint64_t s[4], const bmpc_proof_shard* shard, uint8_t* proof_out,
+                        uint8_t* partials_out, int* statuses_out) {
     if (!P->h || !P->l || !P->a || !P->b_g1 || !P->b_g2) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
@@ -651,11 +660,13 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
     uint8_t vkraw[672];
     memcpy(vkraw, P->alpha_g1, 96); memcpy(vkraw + 96, P->beta_g1, 96); memcpy(vkraw + 192, P->delta_g1, 96);
     memcpy(vkraw + 288, P->beta_g2, 192); memcpy(vkraw + 480, P->delta_g2, 192);
-    CKP(cudaMemcpyAsync(d_vkraw, vkraw, 672, cudaMemcpyHostToDevice, st));
-    CKP(cudaMemcpyAsync(d_rs, r, 32, cudaMemcpyHostToDevice, st));
-    CKP(cudaMemcpyAsync(d_rs + 1, s, 32, cudaMemcpyHostToDevice, st));
-    RCP(GroupOps<Fp>::decode(ctx, d_vkraw, 96, 3, vk_g1, st));
-    RCP(GroupOps<Fp2>::decode(ctx, d_vkraw + 288, 192, 2, vk_g2, st));
+    if (!shard) {
+        CKP(cudaMemcpyAsync(d_vkraw, vkraw, 672, cudaMemcpyHostToDevice, st));
+        CKP(cudaMemcpyAsync(d_rs, r, 32, cudaMemcpyHostToDevice, st));
+        CKP(cudaMemcpyAsync(d_rs + 1, s, 32, cudaMemcpyHostToDevice, st));
+        RCP(GroupOps<Fp>::decode(ctx, d_vkraw, 96, 3, vk_g1, st));
+        RCP(GroupOps<Fp2>::decode(ctx, d_vkraw + 288, 192, 2, vk_g2, st));
+    }
 
     // to_le_bits of the assignments (prover.rs:237-250)
     RCP(fr_pointwise(ctx, 2, d_in, nullptr, ni, st));
@@ -664,16 +675,27 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
     // the eight multiexps (prover.rs:233,252-307); statuses resolved in the reference's await order
     size_t b_in_total = 0;
     for (size_t i = 0; i < ni; i++) b_in_total += (S->b_input_density[i / 64] >> (i % 64)) & 1;
+    size_t boff[8] = {0, ni, 0, b_in_total, 0, b_in_total, 0, 0};
+    size_t h_lo = 0, h_hi = m - 1;
+    if (shard) {
+        for (int j = 0; j < 8; j++) boff[j] = shard->base_offset[j];
+        h_lo = shard->h_lo;
+        h_hi = shard->h_hi;
+        if (h_lo > h_hi || h_hi > m - 1) {
+            cleanup();
+            return BMPC_ERR_INVALID;
+        }
+    }
     struct Job { const bmpc_bases* bases; size_t off; const uint64_t* sc; size_t n; const uint64_t* dens; void* out; };
     Job jobs[8] = {
-        {P->a, 0, (uint64_t*)d_in, ni, nullptr, part_g1 + 0},            // a_inputs   :264-269
-        {P->a, ni, (uint64_t*)d_aux, na, d_da, part_g1 + 1},             // a_aux      :270-275
-        {P->b_g1, 0, (uint64_t*)d_in, ni, d_dbi, part_g1 + 2},           // b_g1_inputs:285-290
-        {P->b_g1, b_in_total, (uint64_t*)d_aux, na, d_dba, part_g1 + 3}, // b_g1_aux   :291-296
-        {P->b_g2, 0, (uint64_t*)d_in, ni, d_dbi, part_g2 + 0},           // b_g2_inputs:301-306
-        {P->b_g2, b_in_total, (uint64_t*)d_aux, na, d_dba, part_g2 + 1}, // b_g2_aux   :307
-        {P->h, 0, (uint64_t*)d_a, m - 1, nullptr, part_g1 + 4},          // h          :233
-        {P->l, 0, (uint64_t*)d_aux, na, nullptr, part_g1 + 5},           // l          :252-257
+        {P->a, boff[0], (uint64_t*)d_in, ni, nullptr, part_g1 + 0},       // a_inputs   :264-269
+        {P->a, boff[1], (uint64_t*)d_aux, na, d_da, part_g1 + 1},         // a_aux      :270-275
+        {P->b_g1, boff[2], (uint64_t*)d_in, ni, d_dbi, part_g1 + 2},      // b_g1_inputs:285-290
+        {P->b_g1, boff[3], (uint64_t*)d_aux, na, d_dba, part_g1 + 3},     // b_g1_aux   :291-296
+        {P->b_g2, boff[4], (uint64_t*)d_in, ni, d_dbi, part_g2 + 0},      // b_g2_inputs:301-306
+        {P->b_g2, boff[5], (uint64_t*)d_aux, na, d_dba, part_g2 + 1},     // b_g2_aux   :307
+        {P->h, boff[6], (uint64_t*)(d_a + h_lo), h_hi - h_lo, nullptr, part_g1 + 4},   // h :233
+        {P->l, boff[7], (uint64_t*)d_aux, na, nullptr, part_g1 + 5},      // l          :252-257
     };
     int statuses[8];
     const int order[8] = {0, 1, 2, 3, 4, 5, 7, 6};  // H last: it needs the uploaded a, b, c
@@ -694,6 +716,15 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
             return rc;
         }
         statuses[j] = rc;
+    }
+    if (shard) {   // one rank's share: hand back the partial sums and statuses, the caller gathers them
+        CKP(cudaMemcpyAsync(ctx->h_stage, part_g1, 2304, cudaMemcpyDeviceToHost, st));
+        CKP(cudaStreamSynchronize(st));
+        memcpy(partials_out, ctx->h_stage, 6 * sizeof(G1XYZZ));
+        memcpy(partials_out + 6 * sizeof(G1XYZZ), ctx->h_stage + 1536, 2 * sizeof(G2XYZZ));
+        for (int j = 0; j < 8; j++) statuses_out[j] = statuses[j];
+        cleanup();
+        return BMPC_OK;
     }
     // subversion check delta != identity comes before the first wait() (prover.rs:309-313)
     if ((P->delta_g1[0] & 0x40) || (P->delta_g2[0] & 0x40)) {
@@ -717,6 +748,66 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
     return BMPC_OK;
 #undef CKP
 #undef RCP
+}
+}  // namespace
+
+extern "C" {
+int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
+                      const uint64_t s[4], uint8_t proof_out[192]) {
+    if (!ctx || !P || !S || !r || !s || !proof_out) return BMPC_ERR_INVALID;
+    return create_proof_common(ctx, P, S, r, s, nullptr, proof_out, nullptr, nullptr);
+}
+
+int bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S,
+                               const bmpc_proof_shard* shard, uint8_t partials_out[BMPC_PROOF_PARTIAL_BYTES],
+                               int statuses_out[8]) {
+    if (!ctx || !P || !S || !shard || !partials_out || !statuses_out) return BMPC_ERR_INVALID;
+    return create_proof_common(ctx, P, S, nullptr, nullptr, shard, nullptr, partials_out, statuses_out);
+}
+
+int bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* P, const uint8_t* partials_all, size_t world,
+                             const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]) {
+    if (!ctx || !P || !partials_all || !world || world > 64 || !r || !s || !proof_out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    // subversion check first, as in the single-GPU path (prover.rs:309-313)
+    if ((P->delta_g1[0] & 0x40) || (P->delta_g2[0] & 0x40)) return BMPC_ERR_UNEXPECTED_IDENTITY;
+    const size_t need = align_up(world * BMPC_PROOF_PARTIAL_BYTES, 256) + 8192;
+    int rr = io_reserve(ctx, need);
+    if (rr) return rr;
+    uint8_t* d_all = reinterpret_cast<uint8_t*>(ctx->io);
+    uint8_t* d_misc = d_all + align_up(world * BMPC_PROOF_PARTIAL_BYTES, 256);
+    G1XYZZ* part_g1 = reinterpret_cast<G1XYZZ*>(d_misc);
+    G2XYZZ* part_g2 = reinterpret_cast<G2XYZZ*>(d_misc + 1536);
+    G1Affine* vk_g1 = reinterpret_cast<G1Affine*>(d_misc + 2560);
+    G2Affine* vk_g2 = reinterpret_cast<G2Affine*>(d_misc + 3072);
+    Fr* d_rs = reinterpret_cast<Fr*>(d_misc + 3584);
+    uint8_t* d_proof = d_misc + 3840;
+    uint8_t* d_vkraw = d_misc + 4096;
+    uint8_t vkraw[672];
+    memcpy(vkraw, P->alpha_g1, 96); memcpy(vkraw + 96, P->beta_g1, 96); memcpy(vkraw + 192, P->delta_g1, 96);
+    memcpy(vkraw + 288, P->beta_g2, 192); memcpy(vkraw + 480, P->delta_g2, 192);
+    CK(cudaMemcpyAsync(d_all, partials_all, world * BMPC_PROOF_PARTIAL_BYTES, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_vkraw, vkraw, 672, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rs, r, 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_rs + 1, s, 32, cudaMemcpyHostToDevice, st));
+    int rc = GroupOps<Fp>::decode(ctx, d_vkraw, 96, 3, vk_g1, st);
+    if (rc) return rc;
+    rc = GroupOps<Fp2>::decode(ctx, d_vkraw + 288, 192, 2, vk_g2, st);
+    if (rc) return rc;
+    rc = prove_fold_partials_launch(ctx, d_all, (uint32_t)world, part_g1, part_g2, st);
+    if (rc) return rc;
+    ProveTailArgs T;
+    T.a_inputs = part_g1 + 0; T.a_aux = part_g1 + 1; T.b1_inputs = part_g1 + 2; T.b1_aux = part_g1 + 3;
+    T.b2_inputs = part_g2 + 0; T.b2_aux = part_g2 + 1; T.h = part_g1 + 4; T.l = part_g1 + 5;
+    T.vk_g1 = vk_g1; T.vk_g2 = vk_g2; T.rs = d_rs; T.proof = d_proof;
+    rc = prove_tail_launch(ctx, T, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_stage, d_proof, 192, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(proof_out, ctx->h_stage, 192);
+    return BMPC_OK;
 }
 
 // ------------------------------------------------------------- Parameters wire format

@@ -5,15 +5,90 @@
 
 #include "internal.h"
 #include "group_kernels.cuh"
+#include "msm_affine.cuh"
 
 namespace bmpc {
 
 template <class F>
+using AffKernel = void (*)(const Affine<F>*, const uint32_t*, const uint4*, const uint32_t*, XYZZ<F>*, Affine<F>*,
+                           uint32_t, uint32_t, uint32_t);
+template <class F>
+static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb) {
+    if (K == 384) return minb == 4 ? msm_accumulate_affine_kernel<F, 384, 4> : msm_accumulate_affine_kernel<F, 384, 1>;
+    return minb == 4 ? msm_accumulate_affine_kernel<F, 128, 4> : msm_accumulate_affine_kernel<F, 128, 1>;
+}
+
+// Batched-affine accumulation pays when there are enough bucket slices to give every resident
+// thread a job of >= 2 slices (fewer: the inversion is not amortised and the XYZZ kernel wins).
+// BMPC_ACC_AFFINE=0 disables it, =1 forces it (tests run both paths on the same inputs).
+template <class F>
+void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
+    const char* e = getenv("BMPC_ACC_AFFINE");
+    int mode = e ? atoi(e) : -1;
+    p.affine = false;
+    if (mode == 0) return;
+    int sms = 148, occ = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    // tuning knobs: threads per block (power of two <= 128), additions per inversion (128 | 384)
+    uint32_t blk = 128;
+    if (getenv("BMPC_AFF_BLOCKDIM")) {
+        uint32_t v = (uint32_t)atoi(getenv("BMPC_AFF_BLOCKDIM"));
+        if (v == 32 || v == 64 || v == 128) blk = v;
+    }
+    // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
+    // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 needs 252 registers either way.
+    p.aff_K = (getenv("BMPC_AFF_KSEL") && atoi(getenv("BMPC_AFF_KSEL")) == 128) ? 128 : 384;
+    p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 1;
+    if (getenv("BMPC_AFF_MINB")) p.aff_minb = atoi(getenv("BMPC_AFF_MINB")) == 4 ? 4 : 1;
+    p.aff_block = blk;
+    size_t smem = 4 * (size_t)blk * sizeof(F);
+    auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)blk, smem);
+    if (occ < 1) occ = 1;
+    size_t resident = (size_t)sms * occ * blk;
+    size_t gmax = BMPC_AFF_G;                      // BMPC_AFF_GMAX: tuning knob (slices per job)
+    if (getenv("BMPC_AFF_GMAX") && atoi(getenv("BMPC_AFF_GMAX")) >= 1 && (size_t)atoi(getenv("BMPC_AFF_GMAX")) < gmax)
+        gmax = (size_t)atoi(getenv("BMPC_AFF_GMAX"));
+    // slices per job: jobs are handed out in waves of `resident` threads, so G is chosen to fill
+    // the last wave (nb ~ number of slices): maximise nb / (ceil(nb / (G resident)) G resident).
+    size_t G = 0;
+    double best = 0;
+    for (size_t cand = 2; cand <= gmax; cand++) {
+        size_t waves = (p.nb + cand * resident - 1) / (cand * resident);
+        double eff = (double)p.nb / ((double)waves * cand * resident);
+        if (p.nb >= cand * resident / 2 && eff >= best - 1e-9) { best = eff; G = cand; }
+    }
+    // Automatic choice (BMPC_ACC_AFFINE unset): only where it was measured to win -- G1 with at least
+    // two waves of jobs (2^23 points and up with window tables: 31.3 vs 36.8 ms at 2^23, 59.5 vs 73.2
+    // at 2^24; a single wave, <= 2^22, ties with the XYZZ kernel; G2 at 2^22 was slower, 86.8 vs 75.1).
+    if (mode != 1 && (sizeof(F) != sizeof(Fp) || p.nb <= gmax * resident)) return;
+    if (G < 2) {
+        if (mode != 1) return;
+        G = getenv("BMPC_AFF_FORCE_G") ? (size_t)atoi(getenv("BMPC_AFF_FORCE_G")) : 2;
+        if (G < 1) G = 1;
+        if (G > BMPC_AFF_G) G = BMPC_AFF_G;
+    }
+    size_t jobs = (p.max_tasks + G - 1) / G;
+    size_t blocks = (jobs + blk - 1) / blk;
+    if (blocks > (size_t)sms * occ) blocks = (size_t)sms * occ;
+    p.affine = true;
+    p.aff_G = (uint32_t)G;
+    p.aff_blocks = (uint32_t)blocks;
+    p.aff_HA = (p.g.L + 1) / 2;
+    p.aff_HB = (p.aff_HA + 1) / 2;
+}
+
+template <class F>
 size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
-    size_t b = ws_need(p.max_tasks, sizeof(XYZZ<F>)) + ws_need((size_t)p.red_H * p.nblk, sizeof(XYZZ<F>)) + 1024;
-    if (p.use2d)
-        b += ws_need((size_t)p.g.H * 2 * p.NT, sizeof(XYZZ<F>)) + ws_need((size_t)p.red_H * p.Bm, sizeof(XYZZ<F>));
-    return b;
+    if (p.affine)
+        return curve_bytes_xyzz(p) + ws_need((size_t)p.aff_blocks * p.aff_block * p.aff_G * (p.aff_HA + p.aff_HB), sizeof(Affine<F>));
+    return curve_bytes_xyzz(p);
+}
+template <class F>
+size_t GroupOps<F>::curve_bytes_xyzz(const MsmPlan& p) {
+    return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + 2 * ws_need((size_t)p.g.H * p.nblk, sizeof(XYZZ<F>)) +
+           ws_need(p.g.H, sizeof(XYZZ<F>)) + ws_need(64, 4) + 1024;
 }
 
 template <class F>
@@ -21,20 +96,28 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
                             int mode, uint8_t* d_out_bytes, void* d_out_xyzz, cudaStream_t st) {
     const MsmGeom& g = p.g;
     XYZZ<F>* partials = ws_take<XYZZ<F>>(ctx, p.max_tasks);
-    XYZZ<F>* blk_out = ws_take<XYZZ<F>>(ctx, (size_t)p.red_H * p.nblk);
-    XYZZ<F>* rc_part = nullptr;
-    XYZZ<F>* rc_sums = nullptr;
-    if (p.use2d) {
-        rc_part = ws_take<XYZZ<F>>(ctx, (size_t)g.H * 2 * p.NT);
-        rc_sums = ws_take<XYZZ<F>>(ctx, (size_t)p.red_H * p.Bm);
-    }
-    if (!partials || !blk_out || (p.use2d && (!rc_part || !rc_sums))) {
+    XYZZ<F>* blk_V = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
+    XYZZ<F>* blk_R = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
+    XYZZ<F>* win = ws_take<XYZZ<F>>(ctx, g.H);
+    uint32_t* ticket = ws_take<uint32_t>(ctx, 64);
+    if (!partials || !blk_V || !blk_R || !win || !ticket) {
         ctx->err = "msm workspace carve failed (curve)";
         return BMPC_ERR_INVALID;
     }
     const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
     uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
-    {
+    if (p.affine) {
+        Affine<F>* scratch = ws_take<Affine<F>>(ctx, (size_t)p.aff_blocks * p.aff_block * p.aff_G * (p.aff_HA + p.aff_HB));
+        if (!scratch) {
+            ctx->err = "msm workspace carve failed (affine scratch)";
+            return BMPC_ERR_INVALID;
+        }
+        ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
+        size_t smem = 4 * (size_t)p.aff_block * sizeof(F);
+        auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);
+        LAUNCH(ctx, kern, p.aff_blocks, p.aff_block, smem, st, pts, s.sorted, s.desc, s.ntasks, partials, scratch,
+               p.aff_HA, p.aff_HB, p.aff_G);
+    } else {
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
         // BMPC_ACC_COMPACT=1 selects the variant whose field products are calls (smaller code)
         static const bool compact = getenv("BMPC_ACC_COMPACT") && atoi(getenv("BMPC_ACC_COMPACT")) != 0;
@@ -52,25 +135,19 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     {
         size_t smem = (size_t)p.rblock * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_reduce_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(128 * sizeof(XYZZ<F>))));
-        dim3 grid(p.nblk, p.red_H);
-        if (p.use2d) {
-            dim3 g1((2 * p.NT + 127) / 128, g.H), g2((2 * p.Bm + 127) / 128, g.H);
-            LAUNCH(ctx, msm_rowcol_kernel<F>, g1, 128, 0, st, (const XYZZ<F>*)partials, s.toff, g.B, p.logC, p.S2, rc_part);
-            LAUNCH(ctx, msm_rowcol_fold_kernel<F>, g2, 128, 0, st, (const XYZZ<F>*)rc_part, g.B, p.logC, p.S2, p.Bm, rc_sums);
-            LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, (const XYZZ<F>*)rc_sums, (const uint32_t*)nullptr,
-                   p.red_B, p.S, blk_out);
-        } else {
-            LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, (const XYZZ<F>*)partials, s.toff, g.B, p.S, blk_out);
-        }
+                                (int)(256 * sizeof(XYZZ<F>))));
+        dim3 grid(p.nblk, g.H);
+        LAUNCH(ctx, msm_reduce_kernel<F>, grid, p.rblock, smem, st, (const XYZZ<F>*)partials, s.toff, g.B, p.s_log,
+               blk_V, blk_R);
     }
     {
-        size_t smem = (size_t)(BMPC_FINAL_THREADS + p.red_H) * sizeof(XYZZ<F>);
+        size_t smem = (size_t)BMPC_FINAL_THREADS * sizeof(XYZZ<F>);
         CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // doublings before adding an even / odd set (see msm_final_kernel)
-        uint32_t into_even = p.use2d ? p.logC : g.c, into_odd = p.use2d ? g.c - p.logC : g.c;
-        LAUNCH(ctx, msm_final_kernel<F>, 1, BMPC_FINAL_THREADS, smem, st, blk_out, p.red_H, p.nblk, into_even,
-               into_odd, mode, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        CK(cudaMemsetAsync(ticket, 0, 4, st));
+        uint32_t m_log = p.s_log, rb = p.rblock;
+        while (rb > 1) { m_log++; rb >>= 1; }
+        LAUNCH(ctx, msm_final_kernel<F>, g.H, BMPC_FINAL_THREADS, smem, st, (const XYZZ<F>*)blk_V, (const XYZZ<F>*)blk_R,
+               g.H, p.nblk, m_log, g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     }
     return BMPC_OK;
 }
@@ -78,7 +155,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
 template <class F>
 int GroupOps<F>::sum_partials(bmpc_ctx* ctx, const void* d_parts, uint32_t count, uint8_t* d_out_bytes,
                               cudaStream_t st) {
-    LAUNCH(ctx, msm_sum_partials_kernel<F>, 1, 1, 0, st, reinterpret_cast<const XYZZ<F>*>(d_parts), count, d_out_bytes);
+    LAUNCH(ctx, msm_sum_partials_kernel<F>, 1, 32, 0, st, reinterpret_cast<const XYZZ<F>*>(d_parts), count, d_out_bytes);
     return BMPC_OK;
 }
 

@@ -136,152 +136,138 @@ __device__ __forceinline__ XYZZ<F> bucket_value(const XYZZ<F>* partials, const u
     return v;
 }
 
-// 6a. Two-dimensional bucket reduction.  With bucket index = r C + col (C = 2^logC columns),
-//   sum_v v B_v = C * sum_r r RowSum_r + sum_col (col + 1) ColSum_col,
-// so the weighted sum over 2^(c-1) buckets becomes two PLAIN sums per bucket (no running-sum
-// dependency, no per-thread scalar multiplication) plus weighted sums over only R + C elements.
-// Thread t < NT sums S consecutive buckets of one row; thread NT + t' sums S rows of one column
-// (consecutive threads -> consecutive columns -> coalesced).  grid = (2 NT / 128, H).
+// 6. Weighted sum of one bucket set: sum_k (k + 1) B_k, with no scalar multiplication anywhere.
+// Thread t owns S = 2^s consecutive buckets [t S, (t+1) S): running sums give
+//   run_t = sum B,   acc_t = sum (local index + 1) B;
+// the thread's buckets really weigh t S more each, and  sum_t t S run_t = S sum_{t>=1} Suf_t  with
+// Suf_t = sum_{i>=t} run_i: an inclusive suffix scan over the block (log2 steps in shared memory),
+// s doublings, and the usual tree.  The block emits V = its weighted sum with block-local weights and
+// R = the plain sum of its buckets; the final kernel repeats the same step over the blocks.
+// (The previous version multiplied run_t by t S with a double-and-add ladder per thread: ~300 cold
+// field products against 28 per bucket -- 2.2 ms for 2^18 buckets.)
+// grid = (nblk, sets), blockDim = rblock (power of two <= 256), smem = rblock * sizeof(XYZZ).
 template <class F>
-__global__ void __launch_bounds__(128)
-msm_rowcol_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uint32_t logC, uint32_t S,
-                  XYZZ<F>* P) {
-    const uint32_t h = blockIdx.y, C = 1u << logC, NT = B / S;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * NT) return;
-    XYZZ<F> acc = XYZZ<F>::identity();
-    if (t < NT) {
-        uint32_t base = h * B + t * S;
-        for (uint32_t q = 0; q < S; q++) {
-            XYZZ<F> v = bucket_value<F>(partials, toff, base + q);
-            acc.add(v);
-        }
-    } else {
-        uint32_t tt = t - NT, col = tt & (C - 1u), i = tt >> logC;
-        uint32_t base = h * B + i * S * C + col;
-        for (uint32_t q = 0; q < S; q++) {
-            XYZZ<F> v = bucket_value<F>(partials, toff, base + q * C);
-            acc.add(v);
-        }
-    }
-    store_struct(P + (size_t)h * 2 * NT + t, acc);
-}
-// 6b. RowSum / ColSum from the partial sums.  Output E holds 2 H sets of Bm entries: set 2h = the
-// columns of bucket set h (weight col + 1), set 2h + 1 = its rows 1 .. R-1 (weight r); unused
-// entries are the identity.  grid = (2 Bm / 128, H).
-template <class F>
-__global__ void __launch_bounds__(128)
-msm_rowcol_fold_kernel(const XYZZ<F>* P, uint32_t B, uint32_t logC, uint32_t S, uint32_t Bm, XYZZ<F>* E) {
-    const uint32_t h = blockIdx.y, C = 1u << logC, R = B >> logC, NT = B / S;
-    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 2 * Bm) return;
-    const XYZZ<F>* Ph = P + (size_t)h * 2 * NT;
-    XYZZ<F> acc = XYZZ<F>::identity();
-    if (e < Bm) {
-        if (e < C)
-            for (uint32_t i = 0; i < R / S; i++) {
-                XYZZ<F> v = load_struct(Ph + NT + (size_t)i * C + e);
-                acc.add(v);
-            }
-    } else {
-        uint32_t r = e - Bm + 1u;
-        if (r < R)
-            for (uint32_t j = 0; j < C / S; j++) {
-                XYZZ<F> v = load_struct(Ph + (size_t)r * (C / S) + j);
-                acc.add(v);
-            }
-    }
-    store_struct(E + (size_t)(2 * h) * Bm + e, acc);
-}
-
-// 6c. Weighted sum of one set: sum_k (k + 1) X_k.  Each thread owns S consecutive entries
-// (running sums + lo * sum correction), block tree in shared memory.  toff == NULL: X is the plain
-// array `partials` (the row/column sums of 6b); otherwise X_k = bucket k through toff.
-// grid = (blocks per set, number of sets).
-template <class F>
-__global__ void __launch_bounds__(128)
-msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uint32_t S,
-                  XYZZ<F>* blk_out) {
+__global__ void __launch_bounds__(256)
+msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uint32_t s_log,
+                  XYZZ<F>* blk_V, XYZZ<F>* blk_R) {
     extern __shared__ uint4 reduce_smem[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(reduce_smem);
-    uint32_t w = blockIdx.y;
-    uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t lo = seg * S;
+    const uint32_t w = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+    const uint32_t S = 1u << s_log;
+    const uint32_t lo = (blockIdx.x * nth + tid) * S;
     XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
     if (lo < B) {
-        uint32_t cnt = (B - lo < S) ? (B - lo) : S;
-        for (uint32_t j = cnt; j > 0; j--) {
-            uint32_t bidx = w * B + lo + j - 1u;  // weight lo + j
-            XYZZ<F> v = toff ? bucket_value<F>(partials, toff, bidx) : load_struct(partials + bidx);
+        for (uint32_t j = S; j > 0; j--) {      // local weight j
+            XYZZ<F> v = bucket_value<F>(partials, toff, w * B + lo + j - 1u);
             run.add(v);
             acc.add(run);
         }
-        if (lo != 0) {
-            XYZZ<F> m = run.mul(&lo, 1);
-            acc.add(m);
-        }
     }
-    sm[threadIdx.x] = acc;
+    // inclusive suffix scan of run over the block
+    sm[tid] = run;
     __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            XYZZ<F> x = sm[threadIdx.x], y = sm[threadIdx.x + s];
-            x.add(y);
-            sm[threadIdx.x] = x;
+    for (uint32_t d = 1; d < nth; d <<= 1) {
+        const bool has = tid + d < nth;
+        XYZZ<F> t = XYZZ<F>::identity();
+        if (has) t = sm[tid + d];
+        __syncthreads();
+        if (has) {
+            run.add(t);
+            sm[tid] = run;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) store_struct(blk_out + (size_t)w * gridDim.x + blockIdx.x, sm[0]);
+    if (tid == 0) store_struct(blk_R + (size_t)w * gridDim.x + blockIdx.x, run);
+    if (tid >= 1) {
+        for (uint32_t q = 0; q < s_log; q++) run = run.dbl();
+        acc.add(run);
+    }
+    __syncthreads();
+    sm[tid] = acc;
+    __syncthreads();
+    for (uint32_t st = nth >> 1; st > 0; st >>= 1) {
+        if (tid < st) {
+            XYZZ<F> x = sm[tid], y = sm[tid + st];
+            x.add(y);
+            sm[tid] = x;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_struct(blk_V + (size_t)w * gridDim.x + blockIdx.x, sm[0]);
 }
 
 // ------------------------------------------------------------------------ 7. final
-// blk_out[H][nblk] -> per-set sums (block tree) -> Horner over the sets (the doubling fold of
-// multiexp.rs:244-249; with precomputed tables only the log2(C) doublings of the 2-D reduction).
+// One block per bucket set: the same suffix-scan step over the set's nblk (<= 256, power of two)
+// block results -- block b's buckets weigh b * 2^m_log more (m_log = log2(rblock S)) -- then the
+// LAST block to finish (ticket) runs Horner over the sets (the doubling fold of
+// multiexp.rs:244-249: c doublings between sets; with precomputed tables H == 1, none).
 // mode 0: canonical affine, uncompressed big-endian bytes to out_bytes
 // mode 1: leave the XYZZ partial in out_xyzz (sharded MSM)
-// Launch: 1 block of FINAL_THREADS threads, dynamic smem = (FINAL_THREADS + H) * sizeof(XYZZ).
-#define BMPC_FINAL_THREADS 64
+// Launch: H blocks of FINAL_THREADS threads, dynamic smem = FINAL_THREADS * sizeof(XYZZ);
+// `win` = H XYZZ slots in global memory, *ticket = 0 on entry.
+#define BMPC_FINAL_THREADS 256
 template <class F>
 __global__ void __launch_bounds__(BMPC_FINAL_THREADS)
-msm_final_kernel(const XYZZ<F>* blk_out, uint32_t H, uint32_t nblk, uint32_t dbl_into_even,
-                 uint32_t dbl_into_odd, int mode, uint8_t* out_bytes, XYZZ<F>* out_xyzz) {
+msm_final_kernel(const XYZZ<F>* blk_V, const XYZZ<F>* blk_R, uint32_t H, uint32_t nblk, uint32_t m_log,
+                 uint32_t c, int mode, XYZZ<F>* win, uint32_t* ticket, uint8_t* out_bytes,
+                 XYZZ<F>* out_xyzz) {
     extern __shared__ uint4 final_smem[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(final_smem);
-    XYZZ<F>* win = sm + BMPC_FINAL_THREADS;
-    for (uint32_t h = 0; h < H; h++) {
-        XYZZ<F> s = XYZZ<F>::identity();
-        for (uint32_t j = threadIdx.x; j < nblk; j += BMPC_FINAL_THREADS) {
-            XYZZ<F> v = load_struct(blk_out + (size_t)h * nblk + j);
-            s.add(v);
-        }
-        sm[threadIdx.x] = s;
+    __shared__ uint32_t last;
+    const uint32_t h = blockIdx.x, tid = threadIdx.x;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    if (tid < nblk) {
+        run = load_struct(blk_R + (size_t)h * nblk + tid);
+        acc = load_struct(blk_V + (size_t)h * nblk + tid);
+    }
+    if (nblk > 1) {
+        sm[tid] = run;
         __syncthreads();
-        for (uint32_t st = BMPC_FINAL_THREADS >> 1; st > 0; st >>= 1) {
-            if (threadIdx.x < st) {
-                XYZZ<F> x = sm[threadIdx.x], y = sm[threadIdx.x + st];
-                x.add(y);
-                sm[threadIdx.x] = x;
+        for (uint32_t d = 1; d < nblk; d <<= 1) {
+            const bool has = tid + d < nblk;
+            XYZZ<F> t = XYZZ<F>::identity();
+            if (has) t = sm[tid + d];
+            __syncthreads();
+            if (has) {
+                run.add(t);
+                sm[tid] = run;
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) win[h] = sm[0];
-        __syncthreads();
-    }
-    if (threadIdx.x != 0) return;
-    XYZZ<F> acc = XYZZ<F>::identity();
-    // Horner from the top set down: before adding set h the accumulator is doubled
-    // dbl_into_even (h even) or dbl_into_odd (h odd) times.  One-dimensional reduction: both = c.
-    // Two-dimensional: sets come in (columns, rows) pairs, rows weigh 2^logC, pairs 2^c apart.
-    for (int h = (int)H - 1; h >= 0; h--) {
-        if (h != (int)H - 1) {
-            uint32_t nd = (h & 1) ? dbl_into_odd : dbl_into_even;
-            for (uint32_t j = 0; j < nd; j++) acc = acc.dbl();
+        if (tid >= 1 && tid < nblk) {
+            for (uint32_t q = 0; q < m_log; q++) run = run.dbl();
+            acc.add(run);
         }
-        XYZZ<F> v = win[h];
-        acc.add(v);
+        __syncthreads();
+        sm[tid] = acc;
+        __syncthreads();
+        for (uint32_t st = nblk >> 1; st > 0; st >>= 1) {
+            if (tid < st) {
+                XYZZ<F> x = sm[tid], y = sm[tid + st];
+                x.add(y);
+                sm[tid] = x;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) acc = sm[0];
     }
-    if (mode == 1) { store_struct(out_xyzz, acc); return; }
-    Affine<F> a = acc.to_affine();
+    if (tid == 0) {
+        store_struct(win + h, acc);
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == H - 1u);
+    }
+    __syncthreads();
+    if (!last || tid != 0) return;
+    __threadfence();
+    XYZZ<F> tot = XYZZ<F>::identity();
+    for (int hh = (int)H - 1; hh >= 0; hh--) {     // Horner from the top set down
+        if (hh != (int)H - 1)
+            for (uint32_t j = 0; j < c; j++) tot = tot.dbl();
+        XYZZ<F> v = load_struct(win + hh);
+        tot.add(v);
+    }
+    if (mode == 1) { store_struct(out_xyzz, tot); return; }
+    Affine<F> a = tot.to_affine();
     encode_uncompressed<F>(a, out_bytes);
 }
 
@@ -323,16 +309,34 @@ msm_precompute_kernel(Affine<F>* tables, size_t n, uint32_t c, uint32_t W) {
     }
 }
 
-// sum of `count` XYZZ partials (one per rank) -> canonical affine bytes
+// sum of `count` XYZZ partials (one per rank) -> canonical affine bytes.  One block of 32 threads:
+// strided loads, shuffle-free shared-memory tree (depth 3 for 8 ranks instead of 8 serial additions).
 template <class F>
-__global__ void msm_sum_partials_kernel(const XYZZ<F>* parts, uint32_t count, uint8_t* out_bytes) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XYZZ<F> acc = XYZZ<F>::identity();
-    for (uint32_t j = 0; j < count; j++) {
-        XYZZ<F> v = load_struct(parts + j);
-        acc.add(v);
+__global__ void __launch_bounds__(32)
+msm_sum_partials_kernel(const XYZZ<F>* parts, uint32_t count, uint8_t* out_bytes) {
+    __shared__ uint4 sp_smem[32 * sizeof(XYZZ<F>) / 16];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(sp_smem);
+    uint32_t width = 1;
+    while (width < count && width < 32u) width <<= 1;
+    if (threadIdx.x < width) {
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t j = threadIdx.x; j < count; j += width) {
+            XYZZ<F> v = load_struct(parts + j);
+            acc.add(v);
+        }
+        sm[threadIdx.x] = acc;
     }
-    Affine<F> a = acc.to_affine();
+    __syncthreads();
+    for (uint32_t st = width >> 1; st > 0; st >>= 1) {
+        if (threadIdx.x < st) {
+            XYZZ<F> x = sm[threadIdx.x], y = sm[threadIdx.x + st];
+            x.add(y);
+            sm[threadIdx.x] = x;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    Affine<F> a = sm[0].to_affine();
     encode_uncompressed<F>(a, out_bytes);
 }
 

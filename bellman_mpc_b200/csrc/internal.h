@@ -214,11 +214,12 @@ struct MsmPlan {
     MsmGeom g;
     uint32_t nb;  // total buckets
     size_t max_pairs, max_tasks;
-    uint32_t tpw, rblock, S, nblk;   // weighted-sum kernel geometry (per set of `red_B` entries)
-    // two-dimensional bucket reduction (use2d): buckets of a set form R x C, C = 2^logC
-    bool use2d;
-    uint32_t logC, S2, NT, Bm;       // S2 buckets per row/col thread, NT = B / S2, Bm = max(R, C)
-    uint32_t red_H, red_B;           // sets / entries per set seen by the weighted-sum kernel
+    // weighted-sum (bucket reduction) geometry per bucket set: each thread owns 2^s_log consecutive
+    // buckets, tpw = B >> s_log threads per set in nblk (<= 256) blocks of rblock (<= 128) threads
+    uint32_t s_log, tpw, rblock, nblk;
+    // batched-affine accumulation (msm_affine.cuh): decided per group in GroupOps::plan_affine
+    bool affine = false;
+    uint32_t aff_G = 0, aff_blocks = 0, aff_block = 128, aff_K = 128, aff_minb = 1, aff_HA = 0, aff_HB = 0;
     size_t sort_bytes;  // scratch for everything except the curve-typed buffers
 };
 
@@ -242,7 +243,10 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
 // -------------------------------------------------- group_g1.cu / group_g2.cu
 template <class F>
 struct GroupOps {
+    // chooses between the XYZZ and the batched-affine accumulate kernel (fills p.affine, p.aff_*)
+    static void plan_affine(bmpc_ctx* ctx, MsmPlan& p);
     static size_t curve_bytes(const MsmPlan& p);
+    static size_t curve_bytes_xyzz(const MsmPlan& p);
     // accumulate -> combine -> reduce -> final.  mode 0: uncompressed bytes to d_out_bytes;
     // mode 1: XYZZ partial to d_out_xyzz.
     static int msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, const MsmSorted& s,
@@ -278,5 +282,7 @@ struct ProveTailArgs {
     uint8_t* proof; // 192 B
 };
 int prove_tail_launch(bmpc_ctx* ctx, const ProveTailArgs& args, cudaStream_t st);
+int prove_fold_partials_launch(bmpc_ctx* ctx, const uint8_t* d_all, uint32_t world, G1XYZZ* out1, G2XYZZ* out2,
+                               cudaStream_t st);
 
 }  // namespace bmpc

@@ -78,44 +78,23 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     p.nb = g.H * g.B;
     p.max_pairs = n * g.W;
     p.max_tasks = p.max_pairs / g.L + p.nb + 1;
-    // reduce: each thread owns S consecutive buckets of one set.  S is chosen so that all H sets
-    // together fill exactly one wave of resident blocks (a second, nearly empty wave doubled the
-    // kernel time): capacity = SMs x resident 128-thread blocks (3 for G1 at 148 regs, 2 for G2).
+    // reduce: each thread owns S = 2^s_log consecutive buckets of one set (msm_reduce_kernel), blocks
+    // of 256 threads.  S is the smallest power of two for which all H sets fit in ONE wave of
+    // resident blocks (a second, nearly empty wave doubles the kernel time; 2 resident 256-thread
+    // blocks per SM at <= 128 registers, 1 for G2) and a set has at most 256 blocks (the final
+    // kernel folds a set's block results with one 256-thread block).  The kernel is latency-bound
+    // (a dependent chain of 2 S + 17 cold additions per thread), so smaller S = shorter.
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 3 : 2) * 128;
-        // two-dimensional reduction for big bucket sets (see msm_rowcol_kernel)
-        // Measured on B200 (2^19 buckets: 1-D 3.35 ms vs 2-D 4.2 ms; 2^21: 6.76 vs 6.73) it does not
-        // beat the running-sum kernel yet, so it is opt-in: BMPC_REDUCE_2D=1.
-        p.use2d = g.B >= 4096 && getenv("BMPC_REDUCE_2D") && atoi(getenv("BMPC_REDUCE_2D")) != 0;
-        p.red_H = g.H;
-        p.red_B = g.B;
-        p.logC = p.S2 = p.NT = p.Bm = 0;
-        if (p.use2d) {
-            p.logC = (g.c - 1) / 2;                       // C = 2^logC <= R
-            uint32_t C = 1u << p.logC, R = g.B >> p.logC;
-            size_t want = ((size_t)2 * g.H * g.B + capacity - 1) / capacity;   // one wave of threads
-            uint32_t S2 = 4;
-            while (S2 < want && S2 < C) S2 <<= 1;
-            p.S2 = S2;
-            p.NT = g.B / S2;
-            p.Bm = R > C ? R : C;
-            p.red_H = 2 * g.H;
-            p.red_B = p.Bm;
-        }
-        size_t total = (size_t)p.red_H * p.red_B;
-        uint32_t S = (uint32_t)((total + capacity - 1) / capacity);
-        if (S < 4) S = 4;
-        if (S > p.red_B) S = p.red_B;
-        p.S = S;
-        p.tpw = (p.red_B + S - 1) / S;           // segments (threads) per set
-        p.rblock = 128;
-        if (p.tpw < 128) {                        // power-of-two block for the in-block tree
-            p.rblock = 1;
-            while (p.rblock < p.tpw) p.rblock <<= 1;
-        }
-        p.nblk = (p.tpw + p.rblock - 1) / p.rblock;
+        size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 2 : 1) * 256;
+        uint32_t s_log = 0;
+        while (s_log < g.c - 1 && (((size_t)g.H * g.B) >> s_log) > capacity) s_log++;
+        while (s_log < g.c - 1 && (g.B >> s_log) > 256u * 256u) s_log++;
+        p.s_log = s_log;
+        p.tpw = g.B >> s_log;
+        p.rblock = p.tpw < 256 ? p.tpw : 256;
+        p.nblk = p.tpw / p.rblock;
     }
     size_t b = 0;
     size_t nw32 = (n + 31) / 32;

@@ -91,6 +91,34 @@ __global__ void prove_tail_kernel(ProveTailArgs A, const G1XYZZ* tmp1, const G2X
     }
 }
 
+// Sharded create_proof: rank partials [world][6 G1 | 2 G2] -> the eight multiexp results.
+// One block per multiexp, thread 0 folds the <= 64 partials (8 on one node).
+__global__ void prove_fold_partials_kernel(const uint8_t* all, uint32_t world, G1XYZZ* out1, G2XYZZ* out2) {
+    if (threadIdx.x != 0) return;
+    const uint32_t j = blockIdx.x;
+    const size_t stride = 6 * sizeof(G1XYZZ) + 2 * sizeof(G2XYZZ);
+    if (j < 6) {
+        G1XYZZ acc = G1XYZZ::identity();
+        for (uint32_t w = 0; w < world; w++) {
+            G1XYZZ v = load_struct(reinterpret_cast<const G1XYZZ*>(all + w * stride) + j);
+            acc.add(v);
+        }
+        store_struct(out1 + j, acc);
+    } else {
+        G2XYZZ acc = G2XYZZ::identity();
+        for (uint32_t w = 0; w < world; w++) {
+            G2XYZZ v = load_struct(reinterpret_cast<const G2XYZZ*>(all + w * stride + 6 * sizeof(G1XYZZ)) + (j - 6));
+            acc.add(v);
+        }
+        store_struct(out2 + (j - 6), acc);
+    }
+}
+int prove_fold_partials_launch(bmpc_ctx* ctx, const uint8_t* d_all, uint32_t world, G1XYZZ* out1, G2XYZZ* out2,
+                               cudaStream_t st) {
+    LAUNCH(ctx, prove_fold_partials_kernel, 8, 32, 0, st, d_all, world, out1, out2);
+    return BMPC_OK;
+}
+
 int prove_tail_launch(bmpc_ctx* ctx, const ProveTailArgs& args, cudaStream_t st) {
     // scratch for the seven products lives in the context's small device stage (offset 2048)
     G1XYZZ* tmp1 = reinterpret_cast<G1XYZZ*>(ctx->d_stage + 2048);   // 6 x 192 B

@@ -67,14 +67,17 @@ def combine_status(statuses):
 
 
 def all_gather_bytes(local: bytes, group=None):
-    """all-gather of equal-length byte strings through torch.distributed (any backend)"""
+    """all-gather of equal-length byte strings through torch.distributed (gloo: host tensors;
+    nccl: staged through the current CUDA device)"""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     t = torch.frombuffer(bytearray(local), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
     outs = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(outs, t, group=group)
-    return [bytes(o.numpy().tobytes()) for o in outs]
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
 
 def sharded_multiexp(partial_fn, fold_fn, n, density_words, base_offset, group=None):
@@ -123,3 +126,119 @@ def gpu_sharded_multiexp(worker, bases_slice, scalars_dev_ptr, n_total, group=No
     out = np.zeros(96 if grp == _lib.G1 else 192, dtype=np.uint8)
     st = lib.bmpc_sum_partials(worker.ctx, grp, parts.data_ptr(), world, out.ctypes.data_as(C.c_void_p), stream)
     return st, out.tobytes()
+
+
+# ------------------------------------------------------------------ create_proof over N GPUs
+# every large multiexp of prover.rs:233,252-307 is sharded by exponent range; rank g
+# keeps only the matching slice of each query vector.  The aux positions are cut at multiples of 64
+# so that a rank's density words are a plain sub-array; the (few) input positions all go to rank 0.
+JOBS = ("a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux", "h", "l")
+
+
+def _popcount_words(words, nbits):
+    return dense_before(words, nbits)
+
+
+class ProofShardPlan:
+    """Which slice of create_proof rank `rank` of `world` runs, and which slice [start, end) of each
+    query vector (h, l, a, b_g1 == b_g2) it must hold.  Densities are fixed per circuit
+    (prover.rs:100-138 sets them during synthesis from the constraint system alone), so the plan
+    -- and with it the CRS distribution -- is computed once per circuit."""
+
+    def __init__(self, num_inputs, num_aux, m, a_aux_words, b_input_words, b_aux_words, world, rank):
+        self.world, self.rank = world, rank
+        self.num_inputs, self.num_aux, self.m = num_inputs, num_aux, m
+        blocks = (num_aux + 63) // 64
+        blo, bhi = shard_range(blocks, world, rank)
+        self.aux_lo, self.aux_hi = min(blo * 64, num_aux), min(bhi * 64, num_aux)
+        self.in_lo, self.in_hi = (0, num_inputs) if rank == 0 else (0, 0)
+        self.h_lo, self.h_hi = shard_range(m - 1, world, rank)
+        a_first = num_inputs + dense_before(a_aux_words, self.aux_lo)
+        a_cnt = dense_before(a_aux_words, self.aux_hi) - dense_before(a_aux_words, self.aux_lo)
+        b_in_total = _popcount_words(b_input_words, num_inputs)
+        b_first = b_in_total + dense_before(b_aux_words, self.aux_lo)
+        b_cnt = dense_before(b_aux_words, self.aux_hi) - dense_before(b_aux_words, self.aux_lo)
+        # slices of the full query vectors held by this rank
+        self.vec = {
+            "h": (self.h_lo, self.h_hi),
+            "l": (self.aux_lo, self.aux_hi),
+            "a": (0 if rank == 0 else a_first, a_first + a_cnt),
+            "b": (0 if rank == 0 else b_first, b_first + b_cnt),
+        }
+        a0, b0 = self.vec["a"][0], self.vec["b"][0]
+        # first base of each multiexp inside the rank's slice (JOBS order)
+        self.base_offset = [0, a_first - a0, 0, b_first - b0, 0, b_first - b0, 0, 0]
+
+    def shard_struct(self):
+        sh = _lib.ProofShard()
+        for j, v in enumerate(self.base_offset):
+            sh.base_offset[j] = v
+        sh.h_lo, sh.h_hi = self.h_lo, self.h_hi
+        return sh
+
+
+def proof_partials(worker, params_slice, assignment, plan):
+    """One rank's share: (1920 partial-sum bytes, [8 statuses]).  `assignment` is the FULL
+    ProvingAssignment (host); the slices are taken here."""
+    import ctypes as C
+    asg = assignment
+    w = worker
+    s = _lib.Assignment()
+    wlo = plan.aux_lo // 64
+    da = np.ascontiguousarray(asg.a_aux_density.words()[wlo:])
+    db = np.ascontiguousarray(asg.b_aux_density.words()[wlo:])
+    dbi = np.ascontiguousarray(asg.b_input_density.words())
+    aux = asg.aux_assignment[plan.aux_lo:plan.aux_hi]
+    inp = asg.input_assignment[plan.in_lo:plan.in_hi]
+    one = np.zeros(1, dtype=np.uint64)
+    ptr = lambda a: C.c_void_p((a if a.size else one).ctypes.data)
+    s.a, s.b, s.c = ptr(asg.a), ptr(asg.b), ptr(asg.c)
+    s.num_constraints = asg.a.shape[0]
+    s.input_assignment, s.num_inputs = ptr(inp), inp.shape[0]
+    s.aux_assignment, s.num_aux = ptr(aux), aux.shape[0]
+    s.a_aux_density, s.b_input_density, s.b_aux_density = ptr(da), ptr(dbi), ptr(db)
+    p = params_slice._struct()
+    sh = plan.shard_struct()
+    out = np.zeros(_lib.PROOF_PARTIAL_BYTES, dtype=np.uint8)
+    st = (C.c_int * 8)()
+    rc = w._lib.bmpc_create_proof_partials(w.ctx, C.byref(p), C.byref(s), C.byref(sh),
+                                           C.c_void_p(out.ctypes.data), C.byref(st))
+    if rc != _lib.OK:
+        return None, [rc] * 8
+    return out.tobytes(), [int(x) for x in st]
+
+
+def proof_finish(worker, params, gathered_partials, statuses_by_rank, r_mont, s_mont):
+    """Fold the ranks' partial sums and run the tail (prover.rs:309-349).  Returns (status, proof):
+    the subversion check on delta comes first, then the multiexp statuses in the order the
+    reference awaits them (prover.rs:328-343), each combined over the ranks."""
+    import ctypes as C
+    w = worker
+    if (params.delta_g1[0] & 0x40) or (params.delta_g2[0] & 0x40):
+        return _lib.ERR_UNEXPECTED_IDENTITY, None
+    for j in range(8):
+        st = combine_status([ranks[j] for ranks in statuses_by_rank])
+        if st != _lib.OK:
+            return st, None
+    world = len(statuses_by_rank)
+    blob = np.frombuffer(b"".join(gathered_partials), dtype=np.uint8)
+    assert blob.size == world * _lib.PROOF_PARTIAL_BYTES
+    p = params._struct()
+    r = np.ascontiguousarray(r_mont, dtype=np.uint64).reshape(4)
+    sv = np.ascontiguousarray(s_mont, dtype=np.uint64).reshape(4)
+    out = np.zeros(192, dtype=np.uint8)
+    rc = w._lib.bmpc_create_proof_finish(w.ctx, C.byref(p), C.c_void_p(blob.ctypes.data), world,
+                                         C.c_void_p(r.ctypes.data), C.c_void_p(sv.ctypes.data),
+                                         C.c_void_p(out.ctypes.data))
+    return rc, (out.tobytes() if rc == _lib.OK else None)
+
+
+def create_proof_sharded(assignment, params_slice, r_mont, s_mont, plan, group=None):
+    """create_proof (prover.rs:206-350) on all ranks of `group`: every rank calls this with its
+    slice of the parameters; every rank gets the 192-byte proof.  One all-gather of 1928 bytes."""
+    partial, statuses = proof_partials(params_slice.worker, params_slice, assignment, plan)
+    local = (partial if partial is not None else bytes(_lib.PROOF_PARTIAL_BYTES)) + bytes(statuses)
+    gathered = all_gather_bytes(local, group)
+    nb = _lib.PROOF_PARTIAL_BYTES
+    return proof_finish(params_slice.worker, params_slice, [g[:nb] for g in gathered],
+                        [list(g[nb:nb + 8]) for g in gathered], r_mont, s_mont)

@@ -364,6 +364,14 @@ def run_ours(args):
         except Exception as e:  # keep the headline line even if the secondary workload fails
             line["prove"] = {"error": repr(e)}
 
+    if world > 1 and not args.no_prove and grp == bm.G1:
+        try:
+            from bench_prove import prove_bench_sharded
+            line["prove"] = prove_bench_sharded(w, args.prove_log_n, max(2, args.steps // 2), world, rank,
+                                                precompute=not args.no_precompute)
+        except Exception as e:
+            line["prove"] = {"error": repr(e)}
+
     # ---- constraint evaluation + key generation on the device
     if world == 1 and not args.no_r1cs and grp == bm.G1:
         try:

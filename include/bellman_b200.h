@@ -205,6 +205,31 @@ typedef struct {
 int  bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assignment* asg,
                        const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
 
+/* create_proof sharded over the GPUs of a node: every multiexp's exponent range is split
+ * into one contiguous slice per rank; the rank holds the matching slice of each query vector.
+ * Order of the eight multiexps everywhere below: a_inputs, a_aux, b_g1_inputs, b_g1_aux,
+ * b_g2_inputs, b_g2_aux, h, l (the order prover.rs:328-343 awaits them, h and l last).
+ *   bmpc_create_proof_partials: `asg` carries the rank's SLICE of the assignment (input/aux
+ *     pointers, counts and density words already offset; a, b, c complete: the H polynomial of
+ *     prover.rs:210-231 is recomputed on every rank, which costs no collective and no more wall
+ *     time than computing it once and scattering it); `params` the rank's slices of the query
+ *     vectors; shard->base_offset[j] = the first base multiexp j consumes inside that slice;
+ *     [h_lo, h_hi) = the rank's share of the m-1 H coefficients.  Returns the eight XYZZ partial
+ *     sums (6 x 192 B G1, then 2 x 384 B G2) and the eight multiexp statuses.
+ *   bmpc_create_proof_finish: `partials_all` = world x BMPC_PROOF_PARTIAL_BYTES gathered from all
+ *     ranks (any collective: 1920 B per rank); folds them, runs prover.rs:309-349, writes the proof.
+ *     The caller combines the statuses first (bellman_mpc_b200/dist.py::combine_status). */
+#define BMPC_PROOF_PARTIAL_BYTES 1920
+typedef struct {
+    size_t base_offset[8];
+    size_t h_lo, h_hi;
+} bmpc_proof_shard;
+int  bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assignment* asg,
+                                const bmpc_proof_shard* shard, uint8_t partials_out[BMPC_PROOF_PARTIAL_BYTES],
+                                int statuses_out[8]);
+int  bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* params, const uint8_t* partials_all, size_t world,
+                              const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
 /* ---- Parameters / VerifyingKey wire format  (src/groth16/mod.rs:146-221,261-400) ------------- */
 typedef struct {
     bmpc_params p;            /* query vectors resident in HBM + the vk points the prover uses    */

@@ -2,10 +2,53 @@
 // algorithms can be checked bit-for-bit against the big-integer oracle without a GPU.
 // Test infrastructure only.
 #include "../../bellman_mpc_b200/csrc/curve.cuh"
+#include "../../bellman_mpc_b200/csrc/msm_affine.cuh"
+#include <vector>
 #include <string.h>
 using namespace bmpc;
 
+// One batched-affine accumulate job (msm_affine.cuh) on the host next to the XYZZ chain it
+// replaces.  tasks: BMPC_AFF_G x {first sorted entry, length}; outputs: per task an affine point
+// (tree result, after XYZZ -> affine) and the chain result.
+template <class F>
+static void affine_job_host(const uint32_t* bases_w, const uint32_t* sorted, const uint32_t* tasks, uint32_t L,
+                            uint32_t* out_tree, uint32_t* out_chain) {
+    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_w);
+    const uint32_t G = BMPC_AFF_G, HA = (L + 1) / 2, HB = (HA + 1) / 2;
+    std::vector<Affine<F>> scratch((size_t)G * (HA + HB));
+    std::vector<XYZZ<F>> partials(G);
+    std::vector<F> pre(BMPC_AFF_K);
+    AffJob<F> J;
+    J.bases = bases; J.sorted = sorted;
+    J.bufA = scratch.data(); J.bufB = scratch.data() + (size_t)G * HA; J.HA = HA; J.HB = HB; J.G = G;
+    for (uint32_t g = 0; g < G; g++) { J.start[g] = tasks[2 * g]; J.len[g] = tasks[2 * g + 1]; J.slot[g] = g; }
+    for (uint32_t g = 0; g < G; g++) partials[g] = XYZZ<F>::identity();
+    aff_run_job<F>(J, pre.data(), (uint32_t)BMPC_AFF_K, partials.data(), SoloCoop());
+    for (uint32_t g = 0; g < G; g++) {
+        Affine<F> t = partials[g].to_affine();
+        memcpy(out_tree + g * sizeof(Affine<F>) / 4, &t, sizeof(Affine<F>));
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t j = 0; j < tasks[2 * g + 1]; j++) {
+            uint32_t e = sorted[tasks[2 * g] + j];
+            Affine<F> p = bases[e & 0x7fffffffu];
+            if (e >> 31) p.y = p.y.neg();
+            acc.add_affine(p);
+        }
+        Affine<F> c = acc.to_affine();
+        memcpy(out_chain + g * sizeof(Affine<F>) / 4, &c, sizeof(Affine<F>));
+    }
+}
+
 extern "C" {
+uint32_t hc_affine_g() { return BMPC_AFF_G; }
+void hc_affine_job_g1(const uint32_t* bases, const uint32_t* sorted, const uint32_t* tasks, uint32_t L,
+                      uint32_t* out_tree, uint32_t* out_chain) {
+    affine_job_host<Fp>(bases, sorted, tasks, L, out_tree, out_chain);
+}
+void hc_affine_job_g2(const uint32_t* bases, const uint32_t* sorted, const uint32_t* tasks, uint32_t L,
+                      uint32_t* out_tree, uint32_t* out_chain) {
+    affine_job_host<Fp2>(bases, sorted, tasks, L, out_tree, out_chain);
+}
 // op: 0 mul, 1 add, 2 sub, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 sqr, 8 inv_fermat
 void hc_fr_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     Fr x, y, z; memcpy(x.l, a, 32); memcpy(y.l, b, 32);

@@ -105,3 +105,39 @@ def test_slicing_helpers():
     s = bdist.slice_density(w, 70, 150)
     assert [bool((int(s[i // 64]) >> (i % 64)) & 1) for i in range(80)] == bits[70:150]
     assert bdist.dense_before(None, 17) == 17 and bdist.slice_density(None, 0, 5) is None
+
+
+def test_proof_shard_plan_covers_the_reference_mapping():
+    """ProofShardPlan: per multiexp, the ranks' (exponent range, first base) pairs tile the
+    reference's single scan (k-th dense exponent consumes base start + k, multiexp.rs:191-222) and
+    the slices of the query vectors are contiguous, disjoint and complete."""
+    import numpy as np
+
+    from bellman_mpc_b200 import dist as bdist
+    rs = np.random.RandomState(3)
+    for ni, na, world in ((2, 645, 2), (16, 1008, 3), (16, 4080, 8), (3, 50, 4)):
+        m = 1
+        while m < ni + na:
+            m *= 2
+        bits = lambda n, p: rs.random_sample(n) < p
+        a_bits, bi_bits, ba_bits = bits(na, 0.75), bits(ni, 0.5), bits(na, 0.5)
+        pack = lambda b: np.packbits(np.concatenate([b, np.zeros((-len(b)) % 64, dtype=bool)]).astype(np.uint8),
+                                     bitorder="little").view(np.uint64)
+        plans = [bdist.ProofShardPlan(ni, na, m, pack(a_bits), pack(bi_bits), pack(ba_bits), world, r)
+                 for r in range(world)]
+        # exponent ranges tile [0, na) and [0, m - 1)
+        assert plans[0].aux_lo == 0 and plans[-1].aux_hi == na and plans[0].h_lo == 0 and plans[-1].h_hi == m - 1
+        for p, q in zip(plans, plans[1:]):
+            assert p.aux_hi == q.aux_lo and p.h_hi == q.h_lo and (p.aux_hi % 64 == 0 or p.aux_hi == na)
+        # vector slices tile the full vectors
+        n_a, n_b = ni + int(a_bits.sum()), int(bi_bits.sum()) + int(ba_bits.sum())
+        for name, total in (("h", m - 1), ("l", na), ("a", n_a), ("b", n_b)):
+            assert plans[0].vec[name][0] == 0 and plans[-1].vec[name][1] == total
+            for p, q in zip(plans, plans[1:]):
+                assert p.vec[name][1] == q.vec[name][0]
+        # a_aux: global base index of the first dense position of each rank
+        for p in plans:
+            glob = ni + int(a_bits[:p.aux_lo].sum())
+            assert p.vec["a"][0] + p.base_offset[1] == glob
+            globb = int(bi_bits.sum()) + int(ba_bits[:p.aux_lo].sum())
+            assert p.vec["b"][0] + p.base_offset[3] == globb == p.vec["b"][0] + p.base_offset[5]

@@ -15,6 +15,16 @@ from util import Q, decode, expected_from_dlogs, known_dlog_bases, rand_scalars
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["xyzz", "affine"])
+def accumulate_kernel(request, monkeypatch):
+    """Every case runs through both bucket-accumulation kernels: the XYZZ chain and the
+    batched-affine tree (msm_affine.cuh; forced here, with 3 slices per job, because the automatic
+    choice only takes it for MSMs that fill the GPU)."""
+    monkeypatch.setenv("BMPC_ACC_AFFINE", "1" if request.param == "affine" else "0")
+    monkeypatch.setenv("BMPC_AFF_FORCE_G", "3")
+    yield request.param
+
+
 def _oracle_points(group, ks):
     G = curves.G1 if group == bm.G1 else curves.G2
     return [G.mul(G.gen, k) if k else None for k in ks]

@@ -90,3 +90,31 @@ def test_synthetic_prove_known_dlog_and_cpu(worker, log_m, profile):
     st, cpu_proof, _ = wl.cpu_reference_proof(threads=4)
     assert st == 0 and cpu_proof == proof
     wl.free()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_sharded_create_proof_emulated(worker, world):
+    """create_proof split over `world` ranks (each holding only its slices of the query
+    vectors) gives the same 192 bytes as the single-GPU call.  The ranks run one after the other on
+    this GPU through the same C-ABI entry points the multi-process path uses
+    (bmpc_create_proof_partials / bmpc_create_proof_finish); the collective is a list append."""
+    import bench_prove
+    from bellman_mpc_b200 import dist as bdist
+    log_m = 10
+    full = bench_prove.Workload(worker, log_m)
+    expect = full.prove()
+    assert expect == full.expected_proof()
+    parts, stats, keep = [], [], []
+    for rank in range(world):
+        wl = bench_prove.Workload(worker, log_m, world=world, rank=rank)
+        pb, st = bdist.proof_partials(worker, wl.params, wl.assignment, wl.plan)
+        assert pb is not None, st
+        parts.append(pb)
+        stats.append(st)
+        keep.append(wl)
+    rc, proof = bdist.proof_finish(worker, keep[0].params, parts, stats, full.r, full.s)
+    assert rc == 0
+    assert proof == expect
+    for wl in keep:
+        wl.free()
+    full.free()

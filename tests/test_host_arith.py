@@ -83,3 +83,58 @@ def test_group_law(lib):
             out = (ctypes.c_uint32 * n)()
             fn(3, enc(pts[4]), enc(None), kl(k), out)
             assert dec(out) == G.mul(pts[4], k)
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_batched_affine_job(lib, which):
+    """msm_affine.cuh's per-thread job (pairwise tree, Montgomery's trick over the chord/tangent
+    denominators) == the XYZZ chain == the oracle's sum, incl. duplicates, opposite points,
+    identity bases, slices of length 0/1/2/3/odd/long (several inversion chunks)."""
+    P, R = fields.Fp.p, fields.Fp.R
+    Ri = pow(R, -1, P)
+    fl = lambda x: [((x * R % P) >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+    fv = lambda l: _v(l) * Ri % P
+    rng = random.Random(5)
+    if which == "g1":
+        G, fn, words = curves.G1, lib.hc_affine_job_g1, 24
+        enc = lambda p: [0] * 24 if p is None else fl(p[0]) + fl(p[1])
+        dec = lambda a: None if not any(a) else (fv(a[:12]), fv(a[12:]))
+    else:
+        G, fn, words = curves.G2, lib.hc_affine_job_g2, 48
+        enc = lambda p: [0] * 48 if p is None else fl(p[0][0]) + fl(p[0][1]) + fl(p[1][0]) + fl(p[1][1])
+        dec = lambda a: None if not any(a) else ((fv(a[:12]), fv(a[12:24])), (fv(a[24:36]), fv(a[36:])))
+    ng = lib.hc_affine_g()
+    nb = 24
+    pts = [G.mul(G.gen, rng.randrange(1, fields.Fr.p)) for _ in range(nb - 1)] + [None]
+    pts[5] = pts[4]                       # duplicate base
+    bases = (ctypes.c_uint32 * (words * nb))(*sum((enc(p) for p in pts), []))
+    L = 300
+    lens = ([0, 1, 2, 3, 5, 8, 13, 300] + [rng.randrange(0, 40) for _ in range(ng)])[:ng]
+    if ng < 8:
+        lens[-1] = 300
+    sorted_entries, tasks = [], []
+    for ln in lens:
+        tasks += [len(sorted_entries), ln]
+        for j in range(ln):
+            r = rng.random()
+            if r < 0.15 and j > 0:
+                e = sorted_entries[-1] ^ 0x80000000          # the negative of the previous point
+            elif r < 0.3 and j > 0:
+                e = sorted_entries[-1]                       # the same point again (tangent case)
+            else:
+                e = rng.randrange(nb) | (rng.randrange(2) << 31)
+            sorted_entries.append(e)
+    # a slice made only of cancelling pairs and identities
+    srt = (ctypes.c_uint32 * max(1, len(sorted_entries)))(*sorted_entries)
+    tk = (ctypes.c_uint32 * (2 * ng))(*tasks)
+    out_tree = (ctypes.c_uint32 * (words * ng))()
+    out_chain = (ctypes.c_uint32 * (words * ng))()
+    fn(bases, srt, tk, L, out_tree, out_chain)
+    tree, chain = list(out_tree), list(out_chain)
+    assert tree == chain
+    for g in range(ng):
+        expect = None
+        for e in sorted_entries[tasks[2 * g]:tasks[2 * g] + tasks[2 * g + 1]]:
+            p = pts[e & 0x7FFFFFFF]
+            expect = G.add(expect, G.neg(p) if e >> 31 else p)
+        assert dec(tree[g * words:(g + 1) * words]) == expect, (which, g)
