@@ -24,7 +24,7 @@ EXPORTS = [
     "bmpc_bases_register", "bmpc_bases_register_dev", "bmpc_bases_precompute", "bmpc_bases_len", "bmpc_bases_group",
     "bmpc_bases_read", "bmpc_bases_dev_ptr", "bmpc_bases_free",
     "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_sum_partials",
-    "bmpc_partial_bytes", "bmpc_msm_geometry",
+    "bmpc_partial_bytes", "bmpc_msm_geometry", "bmpc_msm_accumulate_info",
     "bmpc_domain_from_coeffs", "bmpc_domain_from_coeffs_dev", "bmpc_domain_len", "bmpc_domain_exp",
     "bmpc_domain_into_coeffs", "bmpc_domain_dev_ptr", "bmpc_domain_free", "bmpc_domain_transform",
     "bmpc_domain_distribute_powers", "bmpc_domain_z", "bmpc_domain_divide_by_z_on_coset",
@@ -108,6 +108,7 @@ def load():
         "bmpc_sum_partials": (i32, [vp, i32, vp, sz, vp, vp]),
         "bmpc_partial_bytes": (sz, [i32]),
         "bmpc_msm_geometry": (i32, [vp, vp, sz, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "bmpc_msm_accumulate_info": (i32, [vp, vp, sz, C.POINTER(u32 * 8)]),
         "bmpc_domain_from_coeffs": (i32, [vp, vp, sz, C.POINTER(vp)]),
         "bmpc_domain_from_coeffs_dev": (i32, [vp, vp, sz, C.POINTER(vp), vp]),
         "bmpc_domain_len": (sz, [vp]),

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "internal.h"
@@ -26,9 +27,20 @@ void write_identity(int group, uint8_t* out) {
     out[0] = 0x40;
 }
 
-int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
-                        const uint64_t* d_scalars, size_t n, const uint64_t* d_density,
-                        size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st) {
+// A multiexp in flight: everything is enqueued on `st`, the flags word (and the result bytes)
+// land in the pinned staging area at `h`; multiexp_collect turns them into the reference's status
+// once the stream has been synchronised.  create_proof enqueues all eight before waiting once.
+struct MsmPending {
+    cudaStream_t st = nullptr;     // nullptr: nothing was launched (n == 0), status OK
+    const uint8_t* h = nullptr;
+    size_t out_bytes = 0;
+    uint8_t* out = nullptr;
+};
+
+int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* d_scalars,
+                     size_t n, const uint64_t* d_density, size_t density_len, uint8_t* out, void* d_partial,
+                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend) {
+    *pend = MsmPending();
     if (!bases || (!out && !d_partial)) return BMPC_ERR_INVALID;
     if (d_density && density_len != n) return BMPC_ERR_LENGTH_MISMATCH;  // multiexp.rs:273-278
     if (bases->n >= ((size_t)1 << 31) || base_offset >= ((size_t)1 << 31) || n >= ((size_t)1 << 31))
@@ -58,12 +70,32 @@ int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offs
     else
         rc = GroupOps<Fp2>::msm_finish(ctx, p, bases, sorted, mode, d_bytes, d_partial, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_stage, ctx->d_stage, 64 + out_bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    uint32_t flags = *reinterpret_cast<uint32_t*>(ctx->h_stage);
+    CK(cudaMemcpyAsync(h_dst, ctx->d_stage, 64 + out_bytes, cudaMemcpyDeviceToHost, st));
+    pend->st = st;
+    pend->h = h_dst;
+    pend->out_bytes = out_bytes;
+    pend->out = out;
+    return BMPC_OK;
+}
+
+// after the stream was synchronised
+int multiexp_collect(const MsmPending& pend) {
+    if (!pend.st) return BMPC_OK;
+    uint32_t flags = *reinterpret_cast<const uint32_t*>(pend.h);
     int status = flags_to_status(flags);
-    if (status == BMPC_OK && out) memcpy(out, ctx->h_stage + 64, out_bytes);
+    if (status == BMPC_OK && pend.out) memcpy(pend.out, pend.h + 64, pend.out_bytes);
     return status;
+}
+
+int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                        const uint64_t* d_scalars, size_t n, const uint64_t* d_density,
+                        size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st) {
+    MsmPending pend;
+    int rc = multiexp_enqueue(ctx, bases, base_offset, d_scalars, n, d_density, density_len, out, d_partial, st,
+                              ctx->h_stage, &pend);
+    if (rc) return rc;
+    if (pend.st) CK(cudaStreamSynchronize(st));
+    return multiexp_collect(pend);
 }
 
 int register_points(bmpc_ctx* ctx, bmpc_bases* b, cudaStream_t st) {
@@ -107,6 +139,8 @@ void bmpc_ctx_destroy(bmpc_ctx* ctx) {
     cudaDeviceSynchronize();
     ntt_free_tables(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->slot1_ws) cudaFree(ctx->slot1_ws);
+    if (ctx->slot1_d_stage) cudaFree(ctx->slot1_d_stage);
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -284,6 +318,18 @@ int bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t
     if (window_bits) *window_bits = p.g.c;
     if (windows) *windows = p.g.W;
     if (bucket_sets) *bucket_sets = p.g.H;
+    return BMPC_OK;
+}
+
+int bmpc_msm_accumulate_info(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t info[8]) {
+    if (!ctx || !bases || !info) return BMPC_ERR_INVALID;
+    DeviceGuard dg(ctx->device);
+    MsmPlan p = msm_make_plan(ctx, bases, n, false);
+    if (bases->group == BMPC_G1) GroupOps<Fp>::plan_affine(ctx, p);
+    else GroupOps<Fp2>::plan_affine(ctx, p);
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    info[0] = p.affine ? 1u : 0u;
+    info[1] = p.aff_G; info[2] = p.aff_K; info[3] = p.aff_blocks; info[4] = p.aff_block; info[5] = p.g.L;
     return BMPC_OK;
 }
 
@@ -615,6 +661,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     cudaStream_t cs = ctx->copy_stream;
     auto cleanup = [&]() {
         cudaStreamSynchronize(cs);
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamSynchronize(st);
     };
 #define CKP(call)                                                            \
@@ -697,10 +744,30 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         {P->h, boff[6], (uint64_t*)(d_a + h_lo), h_hi - h_lo, nullptr, part_g1 + 4},   // h :233
         {P->l, boff[7], (uint64_t*)d_aux, na, nullptr, part_g1 + 5},      // l          :252-257
     };
+    // All eight are enqueued before anything is awaited.  The two G2 multiexps run on a second
+    // stream with their own scratch arena and staging words (slot 1), so that their kernels fill the
+    // multiplier-pipe bubbles of the G1 chain (sort: atomics-bound; bucket reduction: latency-bound)
+    // and vice versa; within a slot the multiexps follow each other in stream order and reuse the
+    // arena.  Flags / results of job j land at h_stage + 256 j.
     int statuses[8];
-    const int order[8] = {0, 1, 2, 3, 4, 5, 7, 6};  // H last: it needs the uploaded a, b, c
+    MsmPending pend[8];
+    const int order[8] = {4, 5, 0, 1, 2, 3, 7, 6};  // G2 first (other stream); H last: it needs a, b, c
+    if (!ctx->aux_stream) {
+        CKP(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CKP(cudaEventCreateWithFlags(&ctx->inputs_ready, cudaEventDisableTiming));
+        CKP(cudaMalloc(&ctx->slot1_d_stage, 4096));
+    }
+    CKP(cudaEventRecord(ctx->inputs_ready, st));
+    CKP(cudaStreamWaitEvent(ctx->aux_stream, ctx->inputs_ready, 0));
+    auto swap_slot = [&]() {    // slot 0 <-> slot 1: scratch arena and device staging
+        std::swap(ctx->ws, ctx->slot1_ws);
+        std::swap(ctx->ws_size, ctx->slot1_ws_size);
+        std::swap(ctx->d_stage, ctx->slot1_d_stage);
+        ctx->ws_used = 0;
+    };
     for (int k = 0; k < 8; k++) {
         int j = order[k];
+        const bool g2 = (j == 4 || j == 5);
         if (j == 6) {
             // H polynomial (prover.rs:210-231)
             CKP(cudaStreamWaitEvent(st, ctx->copy_done, 0));
@@ -709,14 +776,19 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
             Fr* t2 = ws_take<Fr>(ctx, m);
             RCP(h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, st));
         }
-        int rc = multiexp_dev_locked(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens,
-                                     jobs[j].n, nullptr, jobs[j].out, st);
-        if (rc == BMPC_ERR_CUDA || rc == BMPC_ERR_INVALID || rc == BMPC_ERR_LENGTH_MISMATCH) {
+        if (g2) swap_slot();
+        int rc = multiexp_enqueue(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens,
+                                  jobs[j].n, nullptr, jobs[j].out, g2 ? ctx->aux_stream : st,
+                                  ctx->h_stage + 256 * j, &pend[j]);
+        if (g2) swap_slot();
+        if (rc != BMPC_OK) {      // argument / launch errors; the multiexp statuses come from the flags
             cleanup();
             return rc;
         }
-        statuses[j] = rc;
     }
+    CKP(cudaStreamSynchronize(ctx->aux_stream));
+    CKP(cudaStreamSynchronize(st));
+    for (int j = 0; j < 8; j++) statuses[j] = multiexp_collect(pend[j]);
     if (shard) {   // one rank's share: hand back the partial sums and statuses, the caller gathers them
         CKP(cudaMemcpyAsync(ctx->h_stage, part_g1, 2304, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));

@@ -51,6 +51,12 @@ struct XYZZ {
         if (COMPACT) return F::mul_cold(a, b);
         return a * b;
     }
+    // square: for Fp2 the inlined path uses complex squaring (2 Fp products instead of 3)
+    template <bool COMPACT>
+    BMPC_HD static F SQ(const F& a) {
+        if (COMPACT) return F::mul_cold(a, a);
+        return a.sqr();
+    }
 
     // 2 * (affine p), p != identity
     template <bool COMPACT>
@@ -97,10 +103,10 @@ struct XYZZ {
             else *this = identity();
             return;
         }
-        F PP = M<COMPACT>(Pd, Pd);
+        F PP = SQ<COMPACT>(Pd);
         F PPP = M<COMPACT>(Pd, PP);
         F Q = M<COMPACT>(X, PP);
-        F X3 = M<COMPACT>(R, R) - PPP - Q.dbl();
+        F X3 = SQ<COMPACT>(R) - PPP - Q.dbl();
         Y = M<COMPACT>(R, Q - X3) - M<COMPACT>(Y, PPP);
         X = X3;
         ZZ = M<COMPACT>(ZZ, PP);

@@ -50,19 +50,21 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     size_t gmax = BMPC_AFF_G;                      // BMPC_AFF_GMAX: tuning knob (slices per job)
     if (getenv("BMPC_AFF_GMAX") && atoi(getenv("BMPC_AFF_GMAX")) >= 1 && (size_t)atoi(getenv("BMPC_AFF_GMAX")) < gmax)
         gmax = (size_t)atoi(getenv("BMPC_AFF_GMAX"));
-    // slices per job: jobs are handed out in waves of `resident` threads, so G is chosen to fill
-    // the last wave (nb ~ number of slices): maximise nb / (ceil(nb / (G resident)) G resident).
+    // Slices per job.  Jobs are handed out in waves of `resident` threads; with a single wave the
+    // kernel's second half runs on a half-empty GPU (threads finish at different times and nothing
+    // refills them), so G is chosen among the values that give at least TWO waves, maximising the
+    // fill of the last one: nb / (ceil(nb / (G resident)) G resident), nb ~ number of slices.
+    // Measured at 2^22 (G1, 2^19 buckets): G = 4 (2 waves) 18.1 ms, G = 7 (1 wave) 20.9 ms, XYZZ 20.1 ms.
     size_t G = 0;
     double best = 0;
     for (size_t cand = 2; cand <= gmax; cand++) {
         size_t waves = (p.nb + cand * resident - 1) / (cand * resident);
         double eff = (double)p.nb / ((double)waves * cand * resident);
-        if (p.nb >= cand * resident / 2 && eff >= best - 1e-9) { best = eff; G = cand; }
+        if (waves >= 2 && eff >= best - 1e-9) { best = eff; G = cand; }
     }
-    // Automatic choice (BMPC_ACC_AFFINE unset): only where it was measured to win -- G1 with at least
-    // two waves of jobs (2^23 points and up with window tables: 31.3 vs 36.8 ms at 2^23, 59.5 vs 73.2
-    // at 2^24; a single wave, <= 2^22, ties with the XYZZ kernel; G2 at 2^22 was slower, 86.8 vs 75.1).
-    if (mode != 1 && (sizeof(F) != sizeof(Fp) || p.nb <= gmax * resident)) return;
+    // Automatic choice (BMPC_ACC_AFFINE unset): where it was measured to win -- enough slices for two
+    // waves of jobs of >= 2 slices (G1: 2^19 buckets and up, i.e. 2^21-point multiexps with window
+    // tables: 18.1 vs 20.1 ms at 2^22, 31.3 vs 36.8 at 2^23, 59.5 vs 73.2 at 2^24; G2 69.7 vs 74.4 at 2^22).
     if (G < 2) {
         if (mode != 1) return;
         G = getenv("BMPC_AFF_FORCE_G") ? (size_t)atoi(getenv("BMPC_AFF_FORCE_G")) : 2;

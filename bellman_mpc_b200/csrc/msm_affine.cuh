@@ -125,6 +125,34 @@ BMPC_HD F aff_fetch_x(const AffJob<F>& J, bool r0, const Affine<F>* src, uint32_
     return aff_ld(&src[(size_t)g * sH + idx].x);
 }
 
+// Round 0 reads its operands through `sorted`: a dependent pair of loads (index, then point).
+// Both passes load the index entries of the NEXT pair before they start multiplying on the
+// current one, so only the point loads are exposed (the index hop was 6.7 % of the stall samples).
+struct AffEntries { uint32_t x, y; };
+template <class F>
+BMPC_HD AffEntries aff_pair_entries(const AffJob<F>& J, uint32_t g, uint32_t i) {
+    AffEntries e;
+    e.x = aff_ldg_u32(J.sorted + J.start[g] + 2 * i);
+    e.y = aff_ldg_u32(J.sorted + J.start[g] + 2 * i + 1);
+    return e;
+}
+template <class F>
+BMPC_HD Affine<F> aff_fetch_e(const AffJob<F>& J, bool r0, uint32_t e, const Affine<F>* src, uint32_t sH, uint32_t g,
+                              uint32_t idx) {
+    if (r0) {
+        Affine<F> p = aff_ldg(J.bases + (e & 0x7fffffffu));
+        if (e & 0x80000000u) p.y = p.y.neg();
+        return p;
+    }
+    return aff_ld(src + (size_t)g * sH + idx);
+}
+template <class F>
+BMPC_HD F aff_fetch_x_e(const AffJob<F>& J, bool r0, uint32_t e, const Affine<F>* src, uint32_t sH, uint32_t g,
+                        uint32_t idx) {
+    if (r0) return aff_ldg(&J.bases[e & 0x7fffffffu].x);
+    return aff_ld(&src[(size_t)g * sH + idx].x);
+}
+
 // 0: chord (d = x2 - x1), 1: tangent (d = 2 y1), 2: no inversion needed
 template <class F>
 BMPC_HD int aff_classify(const Affine<F>& P, const Affine<F>& Q, F& d) {
@@ -174,34 +202,52 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
             F acc = F::one();
             uint32_t cnt = 0;
 #pragma unroll 1
+            AffEntries e = {0u, 0u};
+            if (r0 && g < G) e = aff_pair_entries<F>(J, g, i);
+#pragma unroll 1
             while (cnt < K && g < G) {
-                F x1 = aff_fetch_x<F>(J, r0, src, sH, g, 2 * i);
-                F x2 = aff_fetch_x<F>(J, r0, src, sH, g, 2 * i + 1);
+                const uint32_t gc = g, ic = i;          // the current pair; (g, i) moves on to the next
+                F x1 = aff_fetch_x_e<F>(J, r0, e.x, src, sH, gc, 2 * ic);
+                F x2 = aff_fetch_x_e<F>(J, r0, e.y, src, sH, gc, 2 * ic + 1);
+                const AffEntries ec = e;
+                i++;
+                while (g < G && i >= (J.len[g] >> 1)) { g++; i = 0; }
+                if (r0 && g < G) e = aff_pair_entries<F>(J, g, i);
                 F d = x2 - x1;
                 bool use = true;
                 if (d.is_zero() || x1.is_zero() || x2.is_zero()) {       // rare
-                    Affine<F> P = aff_fetch<F>(J, r0, src, sH, g, 2 * i);
-                    Affine<F> Q = aff_fetch<F>(J, r0, src, sH, g, 2 * i + 1);
+                    Affine<F> P = aff_fetch_e<F>(J, r0, ec.x, src, sH, gc, 2 * ic);
+                    Affine<F> Q = aff_fetch_e<F>(J, r0, ec.y, src, sH, gc, 2 * ic + 1);
                     use = aff_classify<F>(P, Q, d) != 2;
                 }
                 aff_st(pre + cnt, acc);
                 if (use) acc = acc * d;
                 cnt++;
-                i++;
-                while (g < G && i >= (J.len[g] >> 1)) { g++; i = 0; }
             }
             F inv = coop.invert(acc);
             // ---- backward: walk the same pairs in reverse
             uint32_t g2 = g, i2 = i;
-#pragma unroll 1
-            for (uint32_t k = cnt; k-- > 0;) {
+            if (cnt) {                                   // step back onto the chunk's last pair
                 if (i2 == 0) {
                     do { g2--; } while ((J.len[g2] >> 1) == 0);
                     i2 = J.len[g2] >> 1;
                 }
                 i2--;
-                Affine<F> P = aff_fetch<F>(J, r0, src, sH, g2, 2 * i2);
-                Affine<F> Q = aff_fetch<F>(J, r0, src, sH, g2, 2 * i2 + 1);
+                if (r0) e = aff_pair_entries<F>(J, g2, i2);
+            }
+#pragma unroll 1
+            for (uint32_t k = cnt; k-- > 0;) {
+                const uint32_t gc = g2, ic = i2;
+                Affine<F> P = aff_fetch_e<F>(J, r0, e.x, src, sH, gc, 2 * ic);
+                Affine<F> Q = aff_fetch_e<F>(J, r0, e.y, src, sH, gc, 2 * ic + 1);
+                if (k > 0) {                             // the pair before this one, and its entries
+                    if (i2 == 0) {
+                        do { g2--; } while ((J.len[g2] >> 1) == 0);
+                        i2 = J.len[g2] >> 1;
+                    }
+                    i2--;
+                    if (r0) e = aff_pair_entries<F>(J, g2, i2);
+                }
                 F d;
                 int kind = aff_classify<F>(P, Q, d);
                 Affine<F> R;
@@ -218,10 +264,10 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
                         num = xx.dbl() + xx;
                     }
                     F lam = num * dinv;
-                    R.x = lam * lam - P.x - Q.x;
+                    R.x = lam.sqr() - P.x - Q.x;
                     R.y = lam * (P.x - R.x) - P.y;
                 }
-                aff_st(dst + (size_t)g2 * dH + i2, R);
+                aff_st(dst + (size_t)gc * dH + ic, R);
             }
         }
         // odd point of each slice moves up unchanged; lengths halve

@@ -62,6 +62,10 @@ def measured_peaks():
             peaks["acc_traffic_bytes"] = float(k["dram__bytes_read.sum"]) * 1e9 + float(k["dram__bytes_write.sum"]) * 1e6
         except Exception:
             pass
+        try:
+            peaks["aff_traffic_bytes"] = float(json.load(open(kp))["msm_accumulate_affine_g1"]["dram_bytes_total"])
+        except Exception:
+            pass
     ip = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
     if os.path.exists(ip):
         try:
@@ -307,14 +311,24 @@ def run_ours(args):
     roofline_int = None
     cw, ww, hh = C.c_uint32(), C.c_uint32(), C.c_uint32()
     lib.bmpc_msm_geometry(w.ctx, bases.handle, n, C.byref(cw), C.byref(ww), C.byref(hh))
+    ainfo = (C.c_uint32 * 8)()
+    lib.bmpc_msm_accumulate_info(w.ctx, bases.handle, n, C.byref(ainfo))
+    affine = bool(ainfo[0])
+    if affine:
+        # batched-affine tree: 6 products per addition (1 running product, 2 to unwind it, slope,
+        # slope^2, y3); the shared inversion and its product tree are overhead, not counted
+        mul_per_add = 6 * (1 if grp == bm.G1 else 3)
+        roofline["kernel"] = "msm_accumulate_affine_kernel<%s>" % ("Fp" if grp == bm.G1 else "Fp2")
+        roofline["traffic"] = peaks.get("aff_traffic_bytes") if (world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute) else None
     if peaks.get("mac32_per_s") and acc_ms:
-        executed = mul_per_add * 300 * ww.value * n   # 8M+2S mixed additions actually issued
+        executed = mul_per_add * 300 * ww.value * n   # field products of the additions actually issued
         ach = executed / (acc_ms * 1e-3)
-        roofline_int = {"kernel": "msm_accumulate_kernel<Fp>", "bound": "int32-mac",
+        roofline_int = {"kernel": roofline["kernel"], "bound": "int32-mac",
                         "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12, "unit": "TMAC32/s",
                         "frac": ach / peaks["mac32_per_s"],
                         "peak_source": "profiles/r01_imad_peak.json (mad.lo.cc/madc.hi.cc chains, measured)",
-                        "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp mul x 300 MAC32 per point",
+                        "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp mul x 300 MAC32 per point"
+                                + (f" (batched-affine tree, {ainfo[1]} slices per job, {ainfo[2]} additions per inversion per thread)" if affine else " (XYZZ mixed addition 8M+2S)"),
                         "survey_model_frac": (G1_MSM_MAC32_PER_POINT if grp == bm.G1 else G2_MSM_MAC32_PER_POINT) * n / (acc_ms * 1e-3) / peaks["mac32_per_s"],
                         "survey_model": "48000 MAC32 per point (SURVEY 8d: fixed 16 windows)"}
 

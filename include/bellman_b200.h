@@ -130,6 +130,10 @@ size_t bmpc_partial_bytes(int group);
  * window bits c, number of windows W (point additions per dense point), bucket sets H */
 int  bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t* window_bits,
                        uint32_t* windows, uint32_t* bucket_sets);
+/* which bucket-accumulation kernel that multiexp runs: info[0] = 1 batched-affine tree
+ * (msm_affine.cuh) | 0 XYZZ chain; info[1] = slices per job, info[2] = additions per inversion per
+ * thread, info[3] = thread blocks, info[4] = threads per block, info[5] = max points per slice */
+int  bmpc_msm_accumulate_info(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t info[8]);
 
 /* ---- EvaluationDomain  (src/domain.rs:21-189) ------------------------------------------ */
 /* from_coeffs (:47-79): pads with zeros to m = 2^exp >= len (m = 1 for len <= 1);
