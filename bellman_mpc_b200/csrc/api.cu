@@ -139,8 +139,11 @@ void bmpc_ctx_destroy(bmpc_ctx* ctx) {
     cudaDeviceSynchronize();
     ntt_free_tables(ctx);
     if (ctx->ws) cudaFree(ctx->ws);
-    if (ctx->slot1_ws) cudaFree(ctx->slot1_ws);
-    if (ctx->slot1_d_stage) cudaFree(ctx->slot1_d_stage);
+    for (auto& sl : ctx->slots) {
+        if (sl.ws) cudaFree(sl.ws);
+        if (sl.d_stage) cudaFree(sl.d_stage);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     if (ctx->io) cudaFree(ctx->io);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -661,7 +664,8 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     cudaStream_t cs = ctx->copy_stream;
     auto cleanup = [&]() {
         cudaStreamSynchronize(cs);
-        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+        for (auto& sl : ctx->slots)
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
         cudaStreamSynchronize(st);
     };
 #define CKP(call)                                                            \
@@ -744,49 +748,61 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         {P->h, boff[6], (uint64_t*)(d_a + h_lo), h_hi - h_lo, nullptr, part_g1 + 4},   // h :233
         {P->l, boff[7], (uint64_t*)d_aux, na, nullptr, part_g1 + 5},      // l          :252-257
     };
-    // All eight are enqueued before anything is awaited.  The two G2 multiexps run on a second
-    // stream with their own scratch arena and staging words (slot 1), so that their kernels fill the
-    // multiplier-pipe bubbles of the G1 chain (sort: atomics-bound; bucket reduction: latency-bound)
-    // and vice versa; within a slot the multiexps follow each other in stream order and reuse the
-    // arena.  Flags / results of job j land at h_stage + 256 j.
+    // All eight are enqueued before anything is awaited, as three chains on three streams, each
+    // with its own scratch arena and staging words (slot 0 = the context's own):
+    //   slot 1: the G2 multiexps            slot 2: H pipeline + H, then the B-G1 multiexps
+    //   slot 0: the A multiexps and L
+    // so that one chain's multiplier-pipe bubbles (sort: atomics-bound; bucket reduction and the
+    // transforms' tails: latency-bound) are filled by the others' accumulate kernels.  Within a
+    // slot the multiexps follow each other in stream order and reuse the arena.  Flags / results
+    // of job j land at h_stage + 256 j.  (One chain, one wait per multiexp: 155 ms at 2^22; G2 on a
+    // second stream: 123 ms.)
     int statuses[8];
     MsmPending pend[8];
-    const int order[8] = {4, 5, 0, 1, 2, 3, 7, 6};  // G2 first (other stream); H last: it needs a, b, c
-    if (!ctx->aux_stream) {
-        CKP(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    const int order[8] = {4, 5, 6, 0, 1, 7, 2, 3};
+    const int slot_of[8] = {0, 0, 2, 2, 1, 1, 2, 0};
+    if (!ctx->slots[0].stream) {
+        for (auto& sl : ctx->slots) {
+            CKP(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            CKP(cudaMalloc(&sl.d_stage, 4096));
+        }
         CKP(cudaEventCreateWithFlags(&ctx->inputs_ready, cudaEventDisableTiming));
-        CKP(cudaMalloc(&ctx->slot1_d_stage, 4096));
     }
     CKP(cudaEventRecord(ctx->inputs_ready, st));
-    CKP(cudaStreamWaitEvent(ctx->aux_stream, ctx->inputs_ready, 0));
-    auto swap_slot = [&]() {    // slot 0 <-> slot 1: scratch arena and device staging
-        std::swap(ctx->ws, ctx->slot1_ws);
-        std::swap(ctx->ws_size, ctx->slot1_ws_size);
-        std::swap(ctx->d_stage, ctx->slot1_d_stage);
+    for (auto& sl : ctx->slots) CKP(cudaStreamWaitEvent(sl.stream, ctx->inputs_ready, 0));
+    auto swap_slot = [&](int k) {    // slot 0 <-> slot k (k = 1, 2): scratch arena and device staging
+        bmpc_ctx::Slot& sl = ctx->slots[k - 1];
+        std::swap(ctx->ws, sl.ws);
+        std::swap(ctx->ws_size, sl.ws_size);
+        std::swap(ctx->d_stage, sl.d_stage);
         ctx->ws_used = 0;
     };
     for (int k = 0; k < 8; k++) {
-        int j = order[k];
-        const bool g2 = (j == 4 || j == 5);
+        const int j = order[k], sk = slot_of[j];
+        cudaStream_t js = sk ? ctx->slots[sk - 1].stream : st;
+        if (sk) swap_slot(sk);
+        int rc = BMPC_OK;
         if (j == 6) {
             // H polynomial (prover.rs:210-231)
-            CKP(cudaStreamWaitEvent(st, ctx->copy_done, 0));
-            RCP(ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr))));
-            Fr* t1 = ws_take<Fr>(ctx, m);
-            Fr* t2 = ws_take<Fr>(ctx, m);
-            RCP(h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, st));
+            cudaError_t e_ = cudaStreamWaitEvent(js, ctx->copy_done, 0);
+            if (e_ != cudaSuccess) rc = BMPC_ERR_CUDA;
+            if (!rc) rc = ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr)));
+            if (!rc) {
+                Fr* t1 = ws_take<Fr>(ctx, m);
+                Fr* t2 = ws_take<Fr>(ctx, m);
+                rc = h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, js);
+            }
         }
-        if (g2) swap_slot();
-        int rc = multiexp_enqueue(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens,
-                                  jobs[j].n, nullptr, jobs[j].out, g2 ? ctx->aux_stream : st,
-                                  ctx->h_stage + 256 * j, &pend[j]);
-        if (g2) swap_slot();
+        if (!rc)
+            rc = multiexp_enqueue(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens, jobs[j].n,
+                                  nullptr, jobs[j].out, js, ctx->h_stage + 256 * j, &pend[j]);
+        if (sk) swap_slot(sk);
         if (rc != BMPC_OK) {      // argument / launch errors; the multiexp statuses come from the flags
             cleanup();
             return rc;
         }
     }
-    CKP(cudaStreamSynchronize(ctx->aux_stream));
+    for (auto& sl : ctx->slots) CKP(cudaStreamSynchronize(sl.stream));
     CKP(cudaStreamSynchronize(st));
     for (int j = 0; j < 8; j++) statuses[j] = multiexp_collect(pend[j]);
     if (shard) {   // one rank's share: hand back the partial sums and statuses, the caller gathers them

@@ -14,7 +14,11 @@ using AffKernel = void (*)(const Affine<F>*, const uint32_t*, const uint4*, cons
                            uint32_t, uint32_t, uint32_t);
 template <class F>
 static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb) {
-    if (K == 384) return minb == 4 ? msm_accumulate_affine_kernel<F, 384, 4> : msm_accumulate_affine_kernel<F, 384, 1>;
+    if (K == 384) {
+        if (minb == 4) return msm_accumulate_affine_kernel<F, 384, 4>;
+        if (minb == 3) return msm_accumulate_affine_kernel<F, 384, 3>;
+        return msm_accumulate_affine_kernel<F, 384, 1>;
+    }
     return minb == 4 ? msm_accumulate_affine_kernel<F, 128, 4> : msm_accumulate_affine_kernel<F, 128, 1>;
 }
 
@@ -39,7 +43,10 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 needs 252 registers either way.
     p.aff_K = (getenv("BMPC_AFF_KSEL") && atoi(getenv("BMPC_AFF_KSEL")) == 128) ? 128 : 384;
     p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 1;
-    if (getenv("BMPC_AFF_MINB")) p.aff_minb = atoi(getenv("BMPC_AFF_MINB")) == 4 ? 4 : 1;
+    if (getenv("BMPC_AFF_MINB")) {
+        int v = atoi(getenv("BMPC_AFF_MINB"));
+        p.aff_minb = (v == 4 || v == 3) ? (uint32_t)v : 1u;
+    }
     p.aff_block = blk;
     size_t smem = 4 * (size_t)blk * sizeof(F);
     auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);

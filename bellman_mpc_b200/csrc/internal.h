@@ -51,13 +51,16 @@ struct bmpc_ctx {
     // scratch arena (grown on demand, reused across calls)
     char* ws = nullptr;
     size_t ws_size = 0, ws_used = 0;
-    // second multiexp slot (create_proof runs the G2 multiexps beside the G1 chain): its own
-    // stream, scratch arena and device staging words
-    cudaStream_t aux_stream = nullptr;
+    // extra multiexp slots (create_proof runs three chains of multiexps side by side): each has its
+    // own stream, scratch arena and device staging words; slot 0 is the context's own
+    struct Slot {
+        cudaStream_t stream = nullptr;
+        char* ws = nullptr;
+        size_t ws_size = 0;
+        uint8_t* d_stage = nullptr;
+    };
+    Slot slots[2];
     cudaEvent_t inputs_ready = nullptr;
-    char* slot1_ws = nullptr;
-    size_t slot1_ws_size = 0;
-    uint8_t* slot1_d_stage = nullptr;
     // device staging for host-pointer entry points (scalars, density words); grow-only so that a
     // prover calling in a loop does not pay cudaMalloc/cudaFree per call
     char* io = nullptr;

@@ -26,17 +26,28 @@ constexpr uint32_t MIN_TOP_BITS = 7;
 
 // Cost model in point additions: n W bucket additions + 7 per bucket for the reduction (measured on
 // B200: 0.30-0.36 ns per accumulated point, 2.3 ns per bucket: 2.5 ms for 2^19 buckets, 6.1 ms for 2^21).
+static double window_cost(size_t n, uint32_t c, bool one_bucket_set) {
+    uint32_t W = 255 / c + 1;
+    double buckets = (double)(one_bucket_set ? 1u : W) * (double)(1u << (c - 1));
+    return (double)n * W + 7.0 * buckets;
+}
 static uint32_t pick_window(size_t n, uint32_t lo, uint32_t hi, bool one_bucket_set) {
     uint32_t best = 0;
     double best_cost = 0;
     for (uint32_t c = lo; c <= hi; c++) {
         if (n >= (1u << 16) && top_window_bits(c) < MIN_TOP_BITS) continue;  // small n: harmless
-        uint32_t W = 255 / c + 1;
-        double buckets = (double)(one_bucket_set ? 1u : W) * (double)(1u << (c - 1));
-        double cost = (double)n * W + 7.0 * buckets;
+        double cost = window_cost(n, c, one_bucket_set);
         if (!best || cost < best_cost) { best = c; best_cost = cost; }
     }
     return best ? best : lo;
+}
+static uint32_t plain_window(size_t n) {
+    uint32_t lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    uint32_t hi = lg > 8 ? lg - 3 : 5, lo = lg > 10 ? lg - 6 : 4;
+    if (hi > 16) hi = 16;
+    if (lo > hi) lo = hi;
+    return pick_window(n, lo, hi, false);
 }
 
 // Window bits for precomputed tables: all windows share one bucket set, so the bucket count can
@@ -55,22 +66,34 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     MsmGeom& g = p.g;
     uint32_t c;
     bool tables = bases->tab_W != 0;
-    if (tables) c = bases->tab_c;
-    else if (ctx->tune_c) c = (uint32_t)ctx->tune_c;
-    else {
-        uint32_t lg = 0;
-        while (((size_t)1 << (lg + 1)) <= n) lg++;
-        uint32_t hi = lg > 8 ? lg - 3 : 5, lo = lg > 10 ? lg - 6 : 4;
-        if (hi > 16) hi = 16;
-        if (lo > hi) lo = hi;
-        c = pick_window(n, lo, hi, false);
+    uint32_t ksets = 1;
+    if (tables) {
+        // The tables' window was sized for the whole vector; a multiexp over a few of its points
+        // (create_proof's input multiexps: 16 exponents against a 2^22-point query vector) would pay
+        // the reduction of 2^19 empty buckets (1.2 ms G1, 3.7 ms G2).  Such a call splits every table
+        // window into k sub-windows of c' = c / k bits: sub-window s of table window t adds table t's
+        // point into bucket set s (k sets of 2^(c'-1) buckets), and the k sets are folded with
+        // (k-1) c' doublings -- instead of the 255 a table-less geometry needs.  k is the divisor of
+        // the table window minimising additions + 7 per bucket + the doublings' latency (one cold
+        // doubling on the serial tail ~ 22 us ~ 6 10^4 accumulated points).
+        double best = window_cost(n, bases->tab_c, true);
+        static const bool subw = !(getenv("BMPC_MSM_SUBWINDOWS") && atoi(getenv("BMPC_MSM_SUBWINDOWS")) == 0);
+        for (uint32_t k = 2; k <= bases->tab_c / 2 && !ctx->tune_c && subw; k++) {
+            if (bases->tab_c % k) continue;
+            uint32_t cs = bases->tab_c / k;
+            double cost = (double)n * (255 / cs + 1) + 7.0 * k * (double)(1u << (cs - 1)) + 6e4 * (k - 1) * cs;
+            if (cost < best) { best = cost; ksets = k; }
+        }
     }
+    if (tables) c = bases->tab_c / ksets;
+    else if (ctx->tune_c) c = (uint32_t)ctx->tune_c;
+    else c = plain_window(n);
     if (c < 2) c = 2;
     if (c > 22) c = 22;
     g.c = c;
     g.W = 255 / c + 1;
     g.B = 1u << (c - 1);
-    g.H = tables ? 1u : g.W;
+    g.H = tables ? ksets : g.W;
     g.tab_stride = tables ? (uint32_t)bases->n : 0u;
     size_t avg = n * (g.W / g.H) / g.B;
     g.L = (uint32_t)(2 * avg < 64 ? 64 : 2 * avg);

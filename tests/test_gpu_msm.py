@@ -207,6 +207,24 @@ def test_precomputed_tables(worker, group, n, c):
     bases.free()
 
 
+@pytest.mark.parametrize("group,c", [(bm.G1, 12), (bm.G1, 10), (bm.G2, 12), (bm.G1, 13)])
+@pytest.mark.parametrize("n", [1, 16, 300])
+def test_precomputed_tables_short_multiexp(worker, group, c, n):
+    """A multiexp over a few points of a table-registered vector (create_proof's input multiexps:
+    16 exponents against a 2^22-point query vector) splits the table window into sub-windows with
+    their own small bucket sets (msm_make_plan); c = 13 is prime and keeps the one-set geometry.
+    Same bytes, incl. an offset into the vector and a density map."""
+    ks = rand_scalars(4000, 60)
+    bases = known_dlog_bases(worker, group, ks).precompute(c)
+    scalars = rand_scalars(n, 61 + n, "mixed" if n > 1 else "uniform")
+    assert _run(worker, bases, 0, bm.FullDensity(), scalars) == expected_from_dlogs(group, ks, scalars)
+    rng = random.Random(62)
+    bits = [rng.random() < 0.6 for _ in range(n)]
+    got = _run(worker, bases, 3000, bm.DensityTracker.from_bits(bits), scalars)
+    assert got == expected_from_dlogs(group, ks, scalars, bits, 3000)
+    bases.free()
+
+
 def test_precomputed_identity_base(worker):
     G = curves.G1
     rng = random.Random(53)
