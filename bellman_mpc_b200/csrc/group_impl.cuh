@@ -40,9 +40,10 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
         if (v == 32 || v == 64 || v == 128) blk = v;
     }
     // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
-    // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 needs 252 registers either way.
+    // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 at 2^22: 168 registers (3 blocks per
+    // SM, 0.9 KB of spills) 60.3 ms, 252 registers (2 blocks) 65.0 ms, XYZZ kernel 72.0 ms.
     p.aff_K = (getenv("BMPC_AFF_KSEL") && atoi(getenv("BMPC_AFF_KSEL")) == 128) ? 128 : 384;
-    p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 1;
+    p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 3;
     if (getenv("BMPC_AFF_MINB")) {
         int v = atoi(getenv("BMPC_AFF_MINB"));
         p.aff_minb = (v == 4 || v == 3) ? (uint32_t)v : 1u;
