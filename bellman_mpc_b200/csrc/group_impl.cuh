@@ -11,7 +11,7 @@ namespace bmpc {
 
 template <class F>
 using AffKernel = void (*)(const Affine<F>*, const uint32_t*, const uint4*, const uint32_t*, XYZZ<F>*, Affine<F>*,
-                           uint32_t, uint32_t, uint32_t);
+                           uint32_t, uint32_t, uint32_t, uint32_t);
 template <class F>
 static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb) {
     if (K == 384) {
@@ -65,10 +65,22 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     // Measured at 2^22 (G1, 2^19 buckets): G = 4 (2 waves) 18.1 ms, G = 7 (1 wave) 20.9 ms, XYZZ 20.1 ms.
     size_t G = 0;
     double best = 0;
-    for (size_t cand = 2; cand <= gmax; cand++) {
-        size_t waves = (p.nb + cand * resident - 1) / (cand * resident);
-        double eff = (double)p.nb / ((double)waves * cand * resident);
-        if (waves >= 2 && eff >= best - 1e-9) { best = eff; G = cand; }
+    // BMPC_AFF_WHOLE_WAVES (default on): the kernel deals the slices over a whole number of waves
+    // (njobs = waves x resident threads), so the fill of the last wave no longer depends on G and G
+    // only sets the amortisation: the largest G <= gmax that still leaves two waves.
+    p.aff_whole_waves = !(getenv("BMPC_AFF_WHOLE_WAVES") && atoi(getenv("BMPC_AFF_WHOLE_WAVES")) == 0);
+    if (p.aff_whole_waves) {
+        size_t per_thread = (p.nb + resident - 1) / resident;      // slices per resident thread
+        G = (per_thread + 1) / 2;                                   // two waves of jobs this size
+        if (G > gmax) G = gmax;
+        if (G < 2) G = 2;
+        if (p.nb <= 2 * resident) G = 0;                            // no two waves of jobs: XYZZ kernel
+    } else {
+        for (size_t cand = 2; cand <= gmax; cand++) {
+            size_t waves = (p.nb + cand * resident - 1) / (cand * resident);
+            double eff = (double)p.nb / ((double)waves * cand * resident);
+            if (waves >= 2 && eff >= best - 1e-9) { best = eff; G = cand; }
+        }
     }
     // Automatic choice (BMPC_ACC_AFFINE unset): where it was measured to win -- enough slices for two
     // waves of jobs of >= 2 slices (G1: 2^19 buckets and up, i.e. 2^21-point multiexps with window
@@ -126,7 +138,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
         size_t smem = 4 * (size_t)p.aff_block * sizeof(F);
         auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);
         LAUNCH(ctx, kern, p.aff_blocks, p.aff_block, smem, st, pts, s.sorted, s.desc, s.ntasks, partials, scratch,
-               p.aff_HA, p.aff_HB, p.aff_G);
+               p.aff_HA, p.aff_HB, p.aff_G, (uint32_t)p.aff_whole_waves);
     } else {
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
         // BMPC_ACC_COMPACT=1 selects the variant whose field products are calls (smaller code)

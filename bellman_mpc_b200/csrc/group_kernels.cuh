@@ -156,12 +156,23 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
     const uint32_t S = 1u << s_log;
     const uint32_t lo = (blockIdx.x * nth + tid) * S;
     XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
-    if (lo < B) {
-        for (uint32_t j = S; j > 0; j--) {      // local weight j
-            XYZZ<F> v = bucket_value<F>(partials, toff, w * B + lo + j - 1u);
+    // The batched-affine accumulate kernel leaves AFFINE bucket sums (ZZ = ZZZ = 1): `run += v` is
+    // then a mixed addition (10 products instead of 14).  Decided per warp so that the lanes never
+    // split over two addition bodies (XYZZ accumulate kernel, folded heavy buckets: general path).
+    const unsigned wmask = __activemask();
+    const F one = F::one();
+    for (uint32_t j = S; j > 0; j--) {      // local weight j
+        XYZZ<F> v = XYZZ<F>::identity();
+        if (lo < B) v = bucket_value<F>(partials, toff, w * B + lo + j - 1u);
+        const bool ident = v.is_identity();
+        const bool aff = ident || (v.ZZ == one && v.ZZZ == one);
+        if (__all_sync(wmask, aff)) {
+            Affine<F> a = ident ? Affine<F>::identity() : Affine<F>{v.X, v.Y};
+            run.add_affine_cold(a);
+        } else {
             run.add(v);
-            acc.add(run);
         }
+        acc.add(run);
     }
     // inclusive suffix scan of run over the block
     sm[tid] = run;

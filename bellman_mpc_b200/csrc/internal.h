@@ -228,7 +228,7 @@ struct MsmPlan {
     // buckets, tpw = B >> s_log threads per set in nblk (<= 256) blocks of rblock (<= 128) threads
     uint32_t s_log, tpw, rblock, nblk;
     // batched-affine accumulation (msm_affine.cuh): decided per group in GroupOps::plan_affine
-    bool affine = false;
+    bool affine = false, aff_whole_waves = false;
     uint32_t aff_G = 0, aff_blocks = 0, aff_block = 128, aff_K = 128, aff_minb = 1, aff_HA = 0, aff_HB = 0;
     size_t sort_bytes;  // scratch for everything except the curve-typed buffers
 };
