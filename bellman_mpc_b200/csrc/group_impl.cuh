@@ -71,7 +71,8 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     p.aff_whole_waves = !(getenv("BMPC_AFF_WHOLE_WAVES") && atoi(getenv("BMPC_AFF_WHOLE_WAVES")) == 0);
     if (p.aff_whole_waves) {
         size_t per_thread = (p.nb + resident - 1) / resident;      // slices per resident thread
-        G = (per_thread + 1) / 2;                                   // two waves of jobs this size
+        size_t waves = getenv("BMPC_AFF_WAVES") && atoi(getenv("BMPC_AFF_WAVES")) >= 1 ? (size_t)atoi(getenv("BMPC_AFF_WAVES")) : 2;
+        G = (per_thread + waves - 1) / waves;                       // `waves` (2) waves of jobs this size
         if (G > gmax) G = gmax;
         if (G < 2) G = 2;
         if (p.nb <= 2 * resident) G = 0;                            // no two waves of jobs: XYZZ kernel

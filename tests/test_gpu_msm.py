@@ -273,13 +273,14 @@ def test_large_known_dlog(worker):
     bases.free()
 
 
-@pytest.mark.parametrize("tables", [False, True])
-def test_hot_buckets_large(worker, tables):
+@pytest.mark.parametrize("tables,log_n", [(False, 18), (True, 18), (True, 20)])
+def test_hot_buckets_large(worker, tables, log_n):
     """boolean-heavy witness shape at 2^18 (SURVEY 8d/4 secondary profile): 35 % zeros, 35 % ones,
     10 % small values, 20 % uniform -- a few buckets receive a large share of the points (task
-    splitting, heavy-bucket combine, warp-aggregated atomics); checked against sum k_i s_i"""
+    splitting, heavy-bucket combine, warp-aggregated atomics), also at 2^20; checked against
+    sum k_i s_i"""
     from oracle import cref
-    n = 1 << 18
+    n = 1 << log_n
     rs = np.random.RandomState(77)
     ks = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
     sc = rs.randint(0, 1 << 62, size=(n, 4), dtype=np.int64).astype(np.uint64)
