@@ -29,6 +29,7 @@ EXPORTS = [
     "bmpc_domain_into_coeffs", "bmpc_domain_dev_ptr", "bmpc_domain_free", "bmpc_domain_transform",
     "bmpc_domain_distribute_powers", "bmpc_domain_z", "bmpc_domain_divide_by_z_on_coset",
     "bmpc_domain_mul_assign", "bmpc_domain_sub_assign", "bmpc_ntt_dev", "bmpc_ntt",
+    "bmpc_ntt_batch_dev", "bmpc_fr_swap01_dev", "bmpc_ntt_fourstep_twiddle_dev", "bmpc_fr_scale_pow_dev",
     "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
     "bmpc_create_proof", "bmpc_create_proof_partials", "bmpc_create_proof_finish", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
@@ -124,6 +125,10 @@ def load():
         "bmpc_domain_sub_assign": (i32, [vp, vp, vp, vp]),
         "bmpc_ntt_dev": (i32, [vp, vp, u32, i32, vp]),
         "bmpc_ntt": (i32, [vp, vp, u32, i32]),
+        "bmpc_ntt_batch_dev": (i32, [vp, vp, u32, u32, i32, vp]),
+        "bmpc_fr_swap01_dev": (i32, [vp, vp, vp, u32, u32, u32, vp]),
+        "bmpc_ntt_fourstep_twiddle_dev": (i32, [vp, vp, u32, u32, u32, u32, i32, vp]),
+        "bmpc_fr_scale_pow_dev": (i32, [vp, vp, sz, u32, u32, i32, vp]),
         "bmpc_h_coefficients": (i32, [vp, vp, vp, vp, sz, vp, C.POINTER(sz)]),
         "bmpc_h_coefficients_dev": (i32, [vp, vp, vp, vp, u32, vp]),
         "bmpc_fr_to_canonical_dev": (i32, [vp, vp, sz, vp]),

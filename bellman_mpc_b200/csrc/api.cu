@@ -482,6 +482,39 @@ int bmpc_ntt_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_m, int op, void
     return ntt_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_m, op, pick_stream(ctx, stream));
 }
 
+int bmpc_ntt_batch_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_n, uint32_t batch, int inverse, void* stream) {
+    if (!ctx || !d_coeffs) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return ntt_batch_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_n, batch, inverse != 0, pick_stream(ctx, stream));
+}
+
+int bmpc_fr_swap01_dev(bmpc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t d0, uint32_t d1, uint32_t d2,
+                       void* stream) {
+    if (!ctx || !d_in || !d_out || d_in == d_out) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return fr_swap01(ctx, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), d0, d1, d2, pick_stream(ctx, stream));
+}
+
+int bmpc_ntt_fourstep_twiddle_dev(bmpc_ctx* ctx, uint64_t* d, uint32_t rows, uint32_t cols, uint32_t row0,
+                                  uint32_t log_m, int inverse, void* stream) {
+    if (!ctx || !d) return BMPC_ERR_INVALID;
+    if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return fr_fourstep_twiddle(ctx, reinterpret_cast<Fr*>(d), rows, cols, row0, log_m, inverse != 0, pick_stream(ctx, stream));
+}
+
+int bmpc_fr_scale_pow_dev(bmpc_ctx* ctx, uint64_t* d, size_t n, uint32_t first, uint32_t log_m, int which,
+                          void* stream) {
+    if (!ctx || !d) return BMPC_ERR_INVALID;
+    if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    return fr_scale_pow(ctx, reinterpret_cast<Fr*>(d), n, first, log_m, which, pick_stream(ctx, stream));
+}
+
 int bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op) {
     if (!ctx || !coeffs) return BMPC_ERR_INVALID;
     if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;

@@ -202,6 +202,12 @@ int fr_scale_zinv(bmpc_ctx* ctx, Fr* a, size_t m, uint32_t logm, cudaStream_t st
 int fr_distribute_powers(bmpc_ctx* ctx, Fr* a, size_t m, const Fr* d_g, cudaStream_t st);
 int fr_eval_z(bmpc_ctx* ctx, const Fr* d_tau, uint32_t logm, Fr* d_out, cudaStream_t st);
 void ntt_free_tables(bmpc_ctx* ctx);
+// pieces of the distributed four-step transform
+int ntt_batch_dev_locked(bmpc_ctx* ctx, Fr* d, uint32_t logn, uint32_t batch, bool inverse, cudaStream_t st);
+int fr_swap01(bmpc_ctx* ctx, const Fr* in, Fr* out, uint32_t d0, uint32_t d1, uint32_t d2, cudaStream_t st);
+int fr_fourstep_twiddle(bmpc_ctx* ctx, Fr* d, uint32_t rows, uint32_t cols, uint32_t row0, uint32_t logm,
+                        bool inverse, cudaStream_t st);
+int fr_scale_pow(bmpc_ctx* ctx, Fr* d, size_t n, uint32_t first, uint32_t logm, int which, cudaStream_t st);
 
 // ------------------------------------------------------------- msm_sort.cu
 enum { MSM_FLAG_EOF = 1, MSM_FLAG_IDENT_ANY = 2, MSM_FLAG_IDENT_TOP = 4 };

@@ -99,14 +99,17 @@ struct NttScale {
 };
 
 // In-place transform of data[0 .. 2^logm); tmp1/tmp2: scratch buffers of the same size.
+// `batch` > 1: that many independent transforms laid out back to back (data and scratch hold
+// batch * 2^logm coefficients).
 static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, bool inverse,
-                   const NttScale& sc, cudaStream_t st) {
+                   const NttScale& sc, cudaStream_t st, uint32_t batch = 1) {
     DomainTables* dt;
     int rc = get_domain(ctx, logm, st, &dt);
     if (rc) return rc;
     NttPassArgs A;
     memset(&A, 0, sizeof(A));
     A.logn = logm;
+    A.batch_stride = (size_t)1 << logm;
     A.small_log = SMALL_LOG;
     A.tw_small = ctx->tw_small[inverse ? 1 : 0];
     PowTable pre{}, post{};
@@ -123,6 +126,7 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
         A.pre_mode = sc.pre_mode; A.pre = pre;
         A.post_mode = sc.post_mode; A.post = post;
         A.post_const = dt->h_consts[sc.post_const_idx];
+        if (batch != 1) return BMPC_ERR_INVALID;
         LAUNCH(ctx, ntt_trivial_kernel, 1, 1, 0, st, A);
         return BMPC_OK;
     }
@@ -162,13 +166,69 @@ static int ntt_run(bmpc_ctx* ctx, Fr* data, Fr* tmp1, Fr* tmp2, uint32_t logm, b
             CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         {
             ProfScope ps(ctx, BMPC_PROF_NTT_PASS, st);
-            LAUNCH(ctx, ntt_pass_kernel, blocks, threads, smem, st, A);
+            LAUNCH(ctx, ntt_pass_kernel, dim3(blocks, batch), threads, smem, st, A);
         }
         src = dst;
         plog += deg;
     }
     if (npass == 1)
-        CK(cudaMemcpyAsync(data, tmp1, ((size_t)1 << logm) * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(data, tmp1, ((size_t)batch << logm) * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    return BMPC_OK;
+}
+
+// ---- pieces of the distributed four-step transform (bellman_mpc_b200/dist.py: DistributedDomain)
+int ntt_batch_dev_locked(bmpc_ctx* ctx, Fr* d, uint32_t logn, uint32_t batch, bool inverse, cudaStream_t st) {
+    if (logn >= 32 || logn == 0 || batch == 0 || batch > 65535) return BMPC_ERR_INVALID;
+    size_t total = (size_t)batch << logn;
+    int rc = ws_reserve(ctx, 2 * ws_need(total, sizeof(Fr)));
+    if (rc) return rc;
+    Fr* t1 = ws_take<Fr>(ctx, total);
+    Fr* t2 = ws_take<Fr>(ctx, total);
+    NttScale plain;
+    return ntt_run(ctx, d, t1, t2, logn, inverse, plain, st, batch);
+}
+
+int fr_swap01(bmpc_ctx* ctx, const Fr* in, Fr* out, uint32_t d0, uint32_t d1, uint32_t d2, cudaStream_t st) {
+    size_t total = (size_t)d0 * d1 * d2;
+    if (!total) return BMPC_OK;
+    if (d2 >= 8) {
+        LAUNCH(ctx, fr_swap01_rows_kernel, (uint32_t)((total + 255) / 256), 256, 0, st, in, out, d0, d1, d2);
+    } else {
+        dim3 grid((d1 + BMPC_TR_TILE - 1) / BMPC_TR_TILE, (d0 + BMPC_TR_TILE - 1) / BMPC_TR_TILE, 1);
+        if (grid.y > 65535) return BMPC_ERR_INVALID;
+        LAUNCH(ctx, fr_swap01_kernel, grid, BMPC_TR_TILE * BMPC_TR_TILE, 0, st, in, out, d0, d1, d2);
+    }
+    return BMPC_OK;
+}
+
+int fr_fourstep_twiddle(bmpc_ctx* ctx, Fr* d, uint32_t rows, uint32_t cols, uint32_t row0, uint32_t logm,
+                        bool inverse, cudaStream_t st) {
+    DomainTables* dt;
+    int rc = get_domain(ctx, logm, st, &dt);
+    if (rc) return rc;
+    PowTable tw;
+    rc = get_table(ctx, dt, logm, inverse ? K_TW_INV : K_TW_FWD, st, &tw);
+    if (rc) return rc;
+    size_t total = (size_t)rows * cols;
+    if (!total) return BMPC_OK;
+    LAUNCH(ctx, fr_fourstep_twiddle_kernel, (uint32_t)((total + 255) / 256), 256, 0, st, d, rows, cols, row0, logm, tw);
+    return BMPC_OK;
+}
+
+// which: 0 = g^i (coset shift), 1 = g^-i / m (inverse coset), 2 = 1 / m (inverse)
+int fr_scale_pow(bmpc_ctx* ctx, Fr* d, size_t n, uint32_t first, uint32_t logm, int which, cudaStream_t st) {
+    DomainTables* dt;
+    int rc = get_domain(ctx, logm, st, &dt);
+    if (rc) return rc;
+    PowTable T{};
+    if (which == 0 || which == 1) {
+        rc = get_table(ctx, dt, logm, which == 0 ? K_G : K_GINV_MINV, st, &T);
+        if (rc) return rc;
+    } else if (which != 2) {
+        return BMPC_ERR_INVALID;
+    }
+    if (!n) return BMPC_OK;
+    LAUNCH(ctx, fr_scale_pow_kernel, (uint32_t)((n + 255) / 256), 256, 0, st, d, n, first, T, (const Fr*)(dt->d_consts + 2));
     return BMPC_OK;
 }
 

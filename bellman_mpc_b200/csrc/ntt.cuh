@@ -39,6 +39,7 @@ struct NttPassArgs {
     int pre_mode, post_mode;
     PowTable pre, post;
     Fr post_const;
+    size_t batch_stride;  // elements between consecutive transforms of a batch (gridDim.y of them)
 };
 
 __device__ __forceinline__ Fr load_fr(const Fr* p) {
@@ -85,12 +86,14 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassArgs A) {
     const uint32_t tile_base = blockIdx.x << A.tile_log;
     const uint32_t pmask = (1u << A.plog) - 1u;
     const uint32_t total = T << deg;              // elements held by the block
+    const Fr* in = A.in + (size_t)blockIdx.y * A.batch_stride;
+    Fr* out = A.out + (size_t)blockIdx.y * A.batch_stride;
 
     for (uint32_t e = tid; e < total; e += nthr) {
         uint32_t il = e & (T - 1u), s = e >> A.tile_log;
         uint32_t i = tile_base + il;
         uint32_t src = i + (s << tlog);
-        Fr v = load_fr(A.in + src);
+        Fr v = load_fr(in + src);
         if (A.pre_mode == SCALE_POW) v = v * pow_lookup(A.pre, src);
         if (A.plog != 0) {
             uint32_t ex = ((i & pmask) * s) << (tlog - A.plog);
@@ -134,8 +137,64 @@ __global__ void __launch_bounds__(1024) ntt_pass_kernel(NttPassArgs A) {
         Fr v = u[(__brev(sp) >> (32u - deg)) * T + il2];
         if (A.post_mode == SCALE_CONST) v = v * A.post_const;
         else if (A.post_mode == SCALE_POW) v = v * pow_lookup(A.post, dst);
-        store_fr(A.out + dst, v);
+        store_fr(out + dst, v);
     }
+}
+
+// ------------------------------------------------- pieces of the distributed four-step transform
+// out[b][a][c] = in[a][b][c] for 32-byte elements, d2 >= 1 consecutive elements moved together
+// (d2 == 1 is a plain d0 x d1 -> d1 x d0 transpose).  32 x 32 tiles of (a, b) go through shared
+// memory so that both the loads (consecutive b) and the stores (consecutive a) are contiguous runs
+// when d2 is small; for d2 >= 32 the c index alone gives coalescing and the tile is 1 x 1 logically.
+#define BMPC_TR_TILE 16
+__global__ void __launch_bounds__(256) fr_swap01_kernel(const Fr* in, Fr* out, uint32_t d0, uint32_t d1, uint32_t d2) {
+    __shared__ uint4 tile[BMPC_TR_TILE][BMPC_TR_TILE + 1][2];
+    const uint32_t tx = threadIdx.x & (BMPC_TR_TILE - 1), ty = threadIdx.x / BMPC_TR_TILE;
+    const uint32_t a0 = blockIdx.y * BMPC_TR_TILE, b0 = blockIdx.x * BMPC_TR_TILE;
+    for (uint32_t c = blockIdx.z; c < d2; c += gridDim.z) {
+        uint32_t a = a0 + ty, b = b0 + tx;
+        if (a < d0 && b < d1) {
+            const uint4* q = reinterpret_cast<const uint4*>(in + ((size_t)a * d1 + b) * d2 + c);
+            tile[ty][tx][0] = q[0];
+            tile[ty][tx][1] = q[1];
+        }
+        __syncthreads();
+        a = a0 + tx; b = b0 + ty;
+        if (a < d0 && b < d1) {
+            uint4* q = reinterpret_cast<uint4*>(out + ((size_t)b * d0 + a) * d2 + c);
+            q[0] = tile[tx][ty][0];
+            q[1] = tile[tx][ty][1];
+        }
+        __syncthreads();
+    }
+}
+// same permutation when the inner run is long: one thread per element, consecutive threads ->
+// consecutive c (coalesced on both sides)
+__global__ void fr_swap01_rows_kernel(const Fr* in, Fr* out, uint32_t d0, uint32_t d1, uint32_t d2) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)d0 * d1 * d2;
+    if (idx >= total) return;
+    uint32_t c = (uint32_t)(idx % d2);
+    size_t ab = idx / d2;
+    uint32_t b = (uint32_t)(ab % d1), a = (uint32_t)(ab / d1);
+    store_fr(out + ((size_t)b * d0 + a) * d2 + c, load_fr(in + idx));
+}
+// d[r][c] *= w^((row0 + r) c), w = omega_m or its inverse (`tw`: powers of w, m = 2^logm):
+// the twiddle step between the column and the row transforms of the four-step decomposition.
+__global__ void fr_fourstep_twiddle_kernel(Fr* d, uint32_t rows, uint32_t cols, uint32_t row0, uint32_t logm,
+                                           PowTable tw) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * cols) return;
+    uint32_t c = (uint32_t)(idx % cols), r = (uint32_t)(idx / cols);
+    uint64_t e = ((uint64_t)(row0 + r) * c) & (((uint64_t)1 << logm) - 1u);
+    if (e) store_fr(d + idx, load_fr(d + idx) * pow_lookup(tw, (uint32_t)e));
+}
+// d[i] *= T[first + i] (coset shift g^i, or g^-i / m), or d[i] *= *k when T.lo == NULL
+__global__ void fr_scale_pow_kernel(Fr* d, size_t n, uint32_t first, PowTable T, const Fr* k) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr f = T.lo ? pow_lookup(T, first + (uint32_t)i) : *k;
+    store_fr(d + i, load_fr(d + i) * f);
 }
 
 // direct[e] = hi[e >> lo_bits] * lo[e & mask]  (expands a two-level table once)

@@ -242,3 +242,149 @@ def create_proof_sharded(assignment, params_slice, r_mont, s_mont, plan, group=N
     nb = _lib.PROOF_PARTIAL_BYTES
     return proof_finish(params_slice.worker, params_slice, [g[:nb] for g in gathered],
                         [list(g[nb:nb + 8]) for g in gathered], r_mont, s_mont)
+
+
+# ----------------------------------------------------------------------------------------------
+# Distributed EvaluationDomain transform ("four-step NTT with an NCCL all-to-all
+# transpose"): the m = 2^log_m coefficients are split over G ranks, rank g holding the contiguous
+# slice [g m/G, (g+1) m/G), and fft / ifft / coset_fft / icoset_fft (src/domain.rs:81-125) produce
+# the same slice of the same output vector as best_fft on one device.
+#
+# With m = R C, j = C j1 + j2 and k = k1 + R k2:
+#   X[k1 + R k2] = sum_j2 w_C^(j2 k2) * [ w_m^(j2 k1) * sum_j1 x[C j1 + j2] w_R^(j1 k1) ]
+# i.e. (T) transpose the R x C matrix so every rank holds whole columns, R-point transforms of the
+# columns, twiddle by w_m^(j2 k1), (T) transpose so every rank holds whole rows k1, C-point
+# transforms, (T) transpose into natural order.  Each (T) is: local block permutation, one
+# all-to-all of equal chunks, local transpose.  The local steps are C-ABI calls (`GpuFrOps`); the
+# exchange is `torch.distributed.all_to_all_single` (NCCL over NVLink; gloo in the CPU tests).
+
+def is_pow2(x):
+    return x >= 1 and (x & (x - 1)) == 0
+
+
+class FourStepPlan:
+    """geometry of the distributed transform: m = R x C with R = 2^ceil(log_m / 2)"""
+
+    def __init__(self, log_m, world):
+        if not is_pow2(world):
+            raise ValueError("distributed transform needs a power-of-two number of ranks")
+        self.log_m, self.world = log_m, world
+        self.log_r = (log_m + 1) // 2
+        self.log_c = log_m - self.log_r
+        self.R, self.C = 1 << self.log_r, 1 << self.log_c
+        if world > self.C or self.log_c < 1:
+            raise ValueError(f"domain 2^{log_m} is too small to split over {world} ranks")
+        self.m = 1 << log_m
+        self.local = self.m // world          # coefficients per rank
+
+
+def _dist_transpose(buf, P, Q, G, ops, all_to_all):
+    """buf = this rank's P/G rows of a P x Q matrix (row-major) -> its Q/G rows of the transpose"""
+    t = ops.swap01(buf, P // G, G, Q // G)        # [P/G][G][Q/G] -> [G][P/G][Q/G]: chunk h goes to rank h
+    r = all_to_all(t) if G > 1 else t             # [G (source)][P/G][Q/G] = all P rows of my Q/G columns
+    return ops.swap01(r, P, Q // G, 1)            # -> [Q/G][P]
+
+
+def distributed_transform(local, plan, rank, op, ops, all_to_all):
+    """One of FFT / IFFT / COSET_FFT / ICOSET_FFT over a domain split across `plan.world` ranks.
+    local: this rank's slice in the buffer type of `ops`; returns the rank's slice of the result.
+    ops: local steps (GpuFrOps, or the oracle-backed ops of the CPU tests); all_to_all(buf) -> buf
+    exchanges `world` equal chunks (chunk h of the input goes to rank h)."""
+    G, R, C = plan.world, plan.R, plan.C
+    inverse = op in (_lib.IFFT, _lib.ICOSET_FFT)
+    first = rank * plan.local
+    if op == _lib.COSET_FFT:
+        ops.scale_pow(local, plan.local, first, plan.log_m, 0)           # distribute_powers(g), :116-119
+    b = _dist_transpose(local, R, C, G, ops, all_to_all)                 # C/G columns of length R
+    ops.ntt_batch(b, plan.log_r, C // G, inverse)
+    ops.twiddle(b, C // G, R, rank * (C // G), plan.log_m, inverse)
+    d = _dist_transpose(b, C, R, G, ops, all_to_all)                     # R/G rows k1 of length C
+    ops.ntt_batch(d, plan.log_c, R // G, inverse)
+    out = _dist_transpose(d, R, C, G, ops, all_to_all)                   # X[k1 + R k2] at row k2, column k1
+    if op == _lib.IFFT:
+        ops.scale_pow(out, plan.local, first, plan.log_m, 2)             # minv, :88-98
+    elif op == _lib.ICOSET_FFT:
+        ops.scale_pow(out, plan.local, first, plan.log_m, 1)             # g^-i / m, :121-125
+    return out
+
+
+class GpuFrOps:
+    """the local steps on this rank's GPU through the C ABI; buffers are torch CUDA tensors of shape
+    (n, 4) uint64 (Montgomery limbs) -- torch only owns the memory and the stream"""
+
+    def __init__(self, worker):
+        import torch
+        self.torch = torch
+        self.lib, self.ctx = worker._lib, worker.ctx
+
+    def _stream(self):
+        # torch's current stream, so the steps are ordered with torch's copies and with NCCL.  The C
+        # ABI reads a NULL stream as "the context's own stream", so torch's default stream (handle 0)
+        # is passed as cudaStreamLegacy (0x1), the explicit name of the same stream.
+        s = self.torch.cuda.current_stream().cuda_stream
+        return s if s else 1
+
+    def _ck(self, rc):
+        if rc != _lib.OK:
+            raise RuntimeError(f"distributed transform step failed: status {rc}: "
+                               f"{(self.lib.bmpc_last_error(self.ctx) or b'').decode()}")
+
+    def swap01(self, t, d0, d1, d2):
+        out = self.torch.empty_like(t)
+        self._ck(self.lib.bmpc_fr_swap01_dev(self.ctx, t.data_ptr(), out.data_ptr(), d0, d1, d2, self._stream()))
+        return out
+
+    def ntt_batch(self, t, log_n, batch, inverse):
+        self._ck(self.lib.bmpc_ntt_batch_dev(self.ctx, t.data_ptr(), log_n, batch, int(inverse), self._stream()))
+
+    def twiddle(self, t, rows, cols, row0, log_m, inverse):
+        self._ck(self.lib.bmpc_ntt_fourstep_twiddle_dev(self.ctx, t.data_ptr(), rows, cols, row0, log_m,
+                                                        int(inverse), self._stream()))
+
+    def scale_pow(self, t, n, first, log_m, which):
+        self._ck(self.lib.bmpc_fr_scale_pow_dev(self.ctx, t.data_ptr(), n, first, log_m, which, self._stream()))
+
+
+def torch_all_to_all(group=None):
+    """all_to_all callable for `distributed_transform` over torch.distributed"""
+    import torch
+    import torch.distributed as dist
+
+    def run(t):
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t, group=group)
+        return out
+    return run
+
+
+class DistributedDomain:
+    """EvaluationDomain (domain.rs:21-125) whose coefficients are split over the ranks of a
+    torch.distributed group: same method names, each rank passes and gets back its contiguous slice."""
+
+    def __init__(self, worker, local, log_m, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group) if world is None else world
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.plan = FourStepPlan(log_m, self.world)
+        if local.shape[0] != self.plan.local:
+            raise AssertionError("local slice length does not match the domain / world size")
+        self.local, self.ops = local, GpuFrOps(worker)
+        self.a2a = torch_all_to_all(group)
+
+    def _t(self, op):
+        self.local = distributed_transform(self.local, self.plan, self.rank, op, self.ops, self.a2a)
+
+    def fft(self, worker=None):
+        self._t(_lib.FFT)
+
+    def ifft(self, worker=None):
+        self._t(_lib.IFFT)
+
+    def coset_fft(self, worker=None):
+        self._t(_lib.COSET_FFT)
+
+    def icoset_fft(self, worker=None):
+        self._t(_lib.ICOSET_FFT)
+
+    def into_coeffs(self):
+        return self.local

@@ -429,6 +429,42 @@ def run_ours(args):
         line["ntt"] = {"op": "EvaluationDomain::fft, coefficients resident, in place", "sweep": ntt,
                        "bytes_per_coeff": 64, "mac32_per_butterfly": 136}
 
+    # ---- distributed EvaluationDomain::fft over the N GPUs (four-step, all-to-all over NCCL), N > 1
+    if world > 1 and not args.no_ntt and (world & (world - 1)) == 0:
+        try:
+            from bellman_mpc_b200 import dist as bdist
+            logm = args.ntt_dist_log
+            plan = bdist.FourStepPlan(logm, world)
+            ops, a2a = bdist.GpuFrOps(w), bdist.torch_all_to_all()
+            local0 = torch.from_numpy(rand_limbs(plan.local, 30 + rank).view(np.int64)).to(dev)
+            for _ in range(2):
+                out = bdist.distributed_transform(local0.clone(), plan, rank, bm.FFT, ops, a2a)
+            # the inverse transform of the result must give the input back on every rank
+            back = bdist.distributed_transform(out.clone(), plan, rank, bm.IFFT, ops, a2a)
+            ok = torch.tensor([int(torch.equal(back, local0))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            reps = 5
+            ins = [local0.clone() for _ in range(reps)]
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for r in range(reps):
+                bdist.distributed_transform(ins[r], plan, rank, bm.FFT, ops, a2a)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_t = float(t.item())
+            m = 1 << logm
+            line["ntt_dist"] = {"op": "EvaluationDomain::fft over a domain split across the GPUs (four-step, 3 all-to-all)",
+                                "log_m": logm, "n_gpus": world, "ms": ms_t, "roundtrip_identical": bool(ok.item()),
+                                "algorithmic_gbs": 64 * m / (ms_t * 1e-3) / 1e9,
+                                "tmac32_per_s": (m // 2) * logm * 136 / (ms_t * 1e-3) / 1e12,
+                                "all_to_all_bytes_per_gpu": 3 * plan.local * 32 * (world - 1) // world}
+            del ins, local0, out, back
+        except Exception as e:
+            line["ntt_dist"] = {"error": repr(e)}
+
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:
@@ -456,6 +492,7 @@ def main():
     ap.add_argument("--no-r1cs", action="store_true")
     ap.add_argument("--r1cs-log-n", type=int, default=18)
     ap.add_argument("--ntt-max-log", type=int, default=26)
+    ap.add_argument("--ntt-dist-log", type=int, default=26)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

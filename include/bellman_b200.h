@@ -164,6 +164,28 @@ int  bmpc_ntt_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_m, int op, voi
 /* Host-buffer convenience: upload, transform, download (what a drop-in `fft(&worker)` does). */
 int  bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op);
 
+/* ---- pieces of the distributed (multi-GPU) transform ----------------------------------------
+ * A domain whose coefficients are split over G GPUs (rank g holds the contiguous slice
+ * [g m/G, (g+1) m/G)) is transformed as a four-step decomposition m = R x C: transpose, R-point
+ * column transforms, twiddle by omega_m^(j2 k1), transpose, C-point row transforms, transpose back
+ * to natural order -- the same outputs as best_fft (src/domain.rs:261-372) on the whole vector.
+ * The exchange between the steps is an all-to-all over NCCL, driven by the host layer
+ * (bellman_mpc_b200/dist.py: DistributedDomain); these entry points are the per-GPU steps. */
+/* `batch` (<= 65535) independent plain transforms of 2^log_n coefficients, laid out back to back,
+ * in place; inverse != 0 uses omega^-1 and does NOT scale by 1/n. */
+int  bmpc_ntt_batch_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_n, uint32_t batch, int inverse, void* stream);
+/* out[b][a][c] = in[a][b][c] over 32-byte coefficients, a < d0, b < d1, c < d2 (d2 == 1: a plain
+ * transpose); in and out must not overlap. */
+int  bmpc_fr_swap01_dev(bmpc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t d0, uint32_t d1, uint32_t d2,
+                        void* stream);
+/* d[r][c] *= w^((row0 + r) c), r < rows, c < cols, w = omega_m (inverse != 0: omega_m^-1), m = 2^log_m */
+int  bmpc_ntt_fourstep_twiddle_dev(bmpc_ctx* ctx, uint64_t* d, uint32_t rows, uint32_t cols, uint32_t row0,
+                                   uint32_t log_m, int inverse, void* stream);
+/* d[i] *= f(first + i), i < n, for the domain of size 2^log_m: which = 0: g^i (distribute_powers
+ * of coset_fft, :116-119), 1: g^-i / m (icoset_fft, :121-125), 2: 1 / m (ifft, :88-98) */
+int  bmpc_fr_scale_pow_dev(bmpc_ctx* ctx, uint64_t* d, size_t n, uint32_t first, uint32_t log_m, int which,
+                           void* stream);
+
 /* ---- H polynomial  (src/groth16/prover.rs:210-231) -------------------------------------- */
 /* a, b, c: evaluations (len x 4 u64 Montgomery, host).  Runs 3 x (ifft, coset_fft),
  * a*b - c, divide_by_z_on_coset, icoset_fft, drops the last coefficient and converts to
