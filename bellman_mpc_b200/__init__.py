@@ -224,6 +224,30 @@ class Bases:
             self.handle = None
 
 
+def list_mul_matrix(list_g1, list_g2, matrix):
+    """mpc.rs:416-457 `list_mul_matrix(list_g1, list_g2, matrix) -> (Vec<G1>, Vec<G2>)`:
+    result[i] = sum_j list[matrix[i][j].1] * matrix[i][j].0 for the rows before the first empty
+    one, identity elsewhere; both results have the lists' length.  `matrix` is the reference's
+    `Vec<Vec<(Fr, usize)>>` with canonical integers for Fr.  The reference panics on an index out
+    of range (matrix taller than the list, column >= list length): AssertionError here."""
+    row_ptr = np.zeros(len(matrix) + 1, dtype=np.uint64)
+    for i, row in enumerate(matrix):
+        row_ptr[i + 1] = row_ptr[i] + len(row)
+    cols = np.array([idx for row in matrix for (_, idx) in row], dtype=np.int64)
+    if cols.size and (cols.min() < 0 or cols.max() >= (1 << 32)):
+        raise AssertionError("index out of bounds")
+    cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    coeffs = ints_to_limbs([cf for row in matrix for (cf, _) in row]) if cols.size else np.zeros((0, 4), np.uint64)
+    out = []
+    for lst in (list_g1, list_g2):
+        h = C.c_void_p()
+        _raise(lst._lib.bmpc_list_mul_matrix(lst.worker.ctx, lst.handle, _ptr(row_ptr), _ptr(cols) if cols.size else None,
+                                             _ptr(coeffs) if cols.size else None, len(matrix), C.byref(h)),
+               lst.worker.ctx)
+        out.append(Bases(lst.worker, h))
+    return tuple(out)
+
+
 # --------------------------------------------------------------------------- density
 class FullDensity:
     """multiexp.rs:95-114"""

@@ -32,6 +32,7 @@ EXPORTS = [
     "bmpc_ntt_batch_dev", "bmpc_fr_swap01_dev", "bmpc_ntt_fourstep_twiddle_dev", "bmpc_fr_scale_pow_dev",
     "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
     "bmpc_create_proof", "bmpc_create_proof_partials", "bmpc_create_proof_finish", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
+    "bmpc_list_mul_matrix",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
     "bmpc_r1cs_eval", "bmpc_generate_parameters",
 ]
@@ -138,6 +139,7 @@ def load():
         "bmpc_create_proof_finish": (i32, [vp, C.POINTER(Params), vp, sz, vp, vp, vp]),
         "bmpc_batch_scalar_mul": (i32, [vp, vp, vp, i32, C.POINTER(vp)]),
         "bmpc_fixed_base_mul": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),
+        "bmpc_list_mul_matrix": (i32, [vp, vp, vp, vp, vp, sz, C.POINTER(vp)]),
         "bmpc_params_read": (i32, [vp, vp, sz, i32, C.POINTER(ParametersFile)]),
         "bmpc_params_write": (i32, [vp, C.POINTER(ParametersFile), vp, sz, C.POINTER(sz)]),
         "bmpc_params_free": (None, [vp, C.POINTER(ParametersFile)]),

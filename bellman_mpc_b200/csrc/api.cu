@@ -1097,6 +1097,52 @@ int bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* s
     return BMPC_OK;
 }
 
+// -------------------------------------------------------------- list x sparse matrix (mpc.rs:416-457)
+int bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* row_ptr, const uint32_t* cols,
+                         const uint64_t* coeffs, size_t n_rows, bmpc_bases** out) {
+    if (!ctx || !list || !row_ptr || !out) return BMPC_ERR_INVALID;
+    const size_t n = list->n;
+    // result[i] for i < matrix.len() indexes a vector of list.len() elements (:428-429, :445):
+    // a matrix taller than the list panics in the reference, and so does a column >= list.len()
+    if (n_rows > n) return BMPC_ERR_LENGTH_MISMATCH;
+    size_t live = 0;                                     // rows before the first empty one (:432-434)
+    while (live < n_rows && row_ptr[live + 1] > row_ptr[live]) live++;
+    const size_t j0 = row_ptr[0], nnz = row_ptr[live] - j0;
+    if (nnz && (!cols || !coeffs)) return BMPC_ERR_INVALID;
+    if (nnz >= ((size_t)1 << 32)) return BMPC_ERR_INVALID;
+    for (size_t j = 0; j < nnz; j++)
+        if (cols[j0 + j] >= n) return BMPC_ERR_LENGTH_MISMATCH;
+    std::vector<uint32_t> rp(live + 1);
+    for (size_t i = 0; i <= live; i++) rp[i] = (uint32_t)(row_ptr[i] - j0);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->own_stream;
+    const size_t pb = list->group == BMPC_G1 ? 96 : 192;
+    uint32_t *d_rp, *d_col, *d_cf;
+    CK(cudaMalloc(&d_rp, (live + 1) * 4));
+    CK(cudaMalloc(&d_col, (nnz ? nnz : 1) * 4));
+    CK(cudaMalloc(&d_cf, (nnz ? nnz : 1) * 32));
+    CK(cudaMemcpyAsync(d_rp, rp.data(), (live + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CK(cudaMemcpyAsync(d_col, cols + j0, nnz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_cf, coeffs + j0 * 4, nnz * 32, cudaMemcpyHostToDevice, st));
+    }
+    bmpc_bases* b = new bmpc_bases();
+    b->group = list->group;
+    b->n = n;
+    CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    int rcb = list->group == BMPC_G1
+                  ? GroupOps<Fp>::list_mul_matrix(ctx, list->d_points, d_rp, d_col, d_cf, live, n, b->d_points, st)
+                  : GroupOps<Fp2>::list_mul_matrix(ctx, list->d_points, d_rp, d_col, d_cf, live, n, b->d_points, st);
+    if (rcb) return rcb;
+    int rc = register_points(ctx, b, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d_rp)); CK(cudaFree(d_col)); CK(cudaFree(d_cf));
+    *out = b;
+    return BMPC_OK;
+}
+
 int bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uint64_t* scalars, size_t n,
                         int scalars_on_device, bmpc_bases** out) {
     if (!ctx || !base || (!scalars && n) || !out || (group != BMPC_G1 && group != BMPC_G2)) return BMPC_ERR_INVALID;

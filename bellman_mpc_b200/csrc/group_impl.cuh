@@ -226,6 +226,17 @@ int GroupOps<F>::batch_mul(bmpc_ctx* ctx, const void* d_in, const uint32_t* d_sc
 }
 
 template <class F>
+int GroupOps<F>::list_mul_matrix(bmpc_ctx* ctx, const void* d_list, const uint32_t* d_row_ptr, const uint32_t* d_col,
+                                 const uint32_t* d_coeffs, size_t live_rows, size_t n_out, void* d_out,
+                                 cudaStream_t st) {
+    if (!n_out) return BMPC_OK;
+    LAUNCH(ctx, list_mul_matrix_kernel<F>, (uint32_t)((n_out + 127) / 128), 128, 0, st,
+           reinterpret_cast<const Affine<F>*>(d_list), d_row_ptr, d_col, d_coeffs, live_rows, n_out,
+           reinterpret_cast<Affine<F>*>(d_out));
+    return BMPC_OK;
+}
+
+template <class F>
 int GroupOps<F>::fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table, const uint32_t* d_scalars,
                                 size_t n, void* d_out, cudaStream_t st) {
     LAUNCH(ctx, fixed_base_table_kernel<F>, 1, 32, 0, st, reinterpret_cast<const Affine<F>*>(d_base),

@@ -481,6 +481,42 @@ batch_scalar_mul_kernel(const Affine<F>* in, const uint32_t* scalars, int per_el
     store_struct(out + i, acc.to_affine());
 }
 
+// ------------------------------------------------------------------ list x sparse matrix
+// out[i] = sum_j coeff[j] * list[col[j]] over row i's entries j in [row_ptr[i], row_ptr[i+1])
+// (reference: mpc.rs:416-457 list_mul_matrix -- a segmented multiexp whose segments are the rows of
+// a QAP matrix, a handful of entries each).  One thread per row, joint double-and-add over the row
+// (the 255 doublings are shared by all its entries); rows >= live_rows (the reference stops at the
+// first empty row, :432-434) and the tail up to the list's length stay the identity.  Canonical
+// affine out.
+template <class F>
+__global__ void __launch_bounds__(128)
+list_mul_matrix_kernel(const Affine<F>* list, const uint32_t* row_ptr, const uint32_t* col, const uint32_t* coeffs,
+                       size_t live_rows, size_t n_out, Affine<F>* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (i < live_rows) {
+        const uint32_t j0 = row_ptr[i], j1 = row_ptr[i + 1];
+        int top = -1;                                   // highest set bit over the row's coefficients
+        for (uint32_t j = j0; j < j1; j++) {
+            if (load_struct(list + col[j]).is_identity()) continue;
+            for (int w = 7; w >= 0 && w * 32 + 31 > top; w--) {
+                uint32_t v = coeffs[(size_t)j * 8 + w];
+                if (v) { int t = w * 32 + 31 - __clz(v); if (t > top) top = t; break; }
+            }
+        }
+        for (int b = top; b >= 0; b--) {
+            acc = acc.dbl();
+            for (uint32_t j = j0; j < j1; j++) {
+                if (!((coeffs[(size_t)j * 8 + (b >> 5)] >> (b & 31)) & 1u)) continue;
+                Affine<F> p = load_struct(list + col[j]);
+                if (!p.is_identity()) acc.add_affine_cold(p);
+            }
+        }
+    }
+    store_struct(out + i, acc.to_affine());
+}
+
 // Fixed-base: table[w][d] = base * (d * 2^(8 w)), d in [0,256), w in [0,32) as XYZZ.
 template <class F>
 __global__ void fixed_base_table_kernel(const Affine<F>* base, XYZZ<F>* table) {

@@ -278,6 +278,10 @@ struct GroupOps {
     static int inf_bitmap(bmpc_ctx* ctx, const void* d_points, size_t n, uint32_t* d_bitmap, cudaStream_t st);
     static int batch_mul(bmpc_ctx* ctx, const void* d_in, const uint32_t* d_scalars, int per_element,
                          size_t n, void* d_out, cudaStream_t st);
+    // mpc.rs:416-457: out[i] = sum_j coeff[j] * list[col[j]] over CSR row i (i < live_rows), identity after
+    static int list_mul_matrix(bmpc_ctx* ctx, const void* d_list, const uint32_t* d_row_ptr, const uint32_t* d_col,
+                               const uint32_t* d_coeffs, size_t live_rows, size_t n_out, void* d_out,
+                               cudaStream_t st);
     static int fixed_base_mul(bmpc_ctx* ctx, const void* d_base, void* d_table, const uint32_t* d_scalars,
                               size_t n, void* d_out, cudaStream_t st);
     // d_tables: [W][n] with table 0 already filled; fills tables 1..W-1 (2^(c w) * P_i, affine)

@@ -306,6 +306,14 @@ int  bmpc_generate_parameters(bmpc_ctx* ctx, const bmpc_csr* At, const bmpc_csr*
 /* out[i] = in[i] * k[i] (per_element = 1) or in[i] * k[0] (per_element = 0); k canonical 4 x u64 */
 int  bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* scalars,
                            int per_element, bmpc_bases** out);
+/* list_mul_matrix (src/groth16/mpc.rs:416-457), one group at a time (the reference runs the same
+ * loop over a G1 and a G2 list): out has list.len() elements, out[i] = sum_j coeffs[j] * list[cols[j]]
+ * over CSR row i (entries row_ptr[i] .. row_ptr[i+1]) for the rows BEFORE the first empty one (the
+ * reference `break`s there, :432-434); every later element is the identity.  coeffs canonical 4 x u64
+ * per entry.  BMPC_ERR_LENGTH_MISMATCH where the reference panics on an index: n_rows > list.len()
+ * or a live column >= list.len(). */
+int  bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* row_ptr,
+                          const uint32_t* cols, const uint64_t* coeffs, size_t n_rows, bmpc_bases** out);
 /* out[i] = base * k[i]; base uncompressed big-endian; scalars canonical (host or device) */
 int  bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uint64_t* scalars,
                          size_t n, int scalars_on_device, bmpc_bases** out);
