@@ -13,7 +13,10 @@ template <class F>
 using AffKernel = void (*)(const Affine<F>*, const uint32_t*, const uint4*, const uint32_t*, XYZZ<F>*, Affine<F>*,
                            uint32_t, uint32_t, uint32_t, uint32_t);
 template <class F>
-static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb) {
+static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb, uint32_t blk = 128) {
+    // 256-thread blocks (BMPC_AFF_BLOCKDIM=256, experiment): half as many block inversions per SM,
+    // two resident blocks instead of four
+    if (blk == 256) return msm_accumulate_affine_kernel<F, 384, 2, 256>;
     if (K == 384) {
         if (minb == 4) return msm_accumulate_affine_kernel<F, 384, 4>;
         if (minb == 3) return msm_accumulate_affine_kernel<F, 384, 3>;
@@ -37,7 +40,7 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     uint32_t blk = 128;
     if (getenv("BMPC_AFF_BLOCKDIM")) {
         uint32_t v = (uint32_t)atoi(getenv("BMPC_AFF_BLOCKDIM"));
-        if (v == 32 || v == 64 || v == 128) blk = v;
+        if (v == 32 || v == 64 || v == 128 || v == 256) blk = v;
     }
     // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
     // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 at 2^22: 168 registers (3 blocks per
@@ -50,7 +53,7 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     }
     p.aff_block = blk;
     size_t smem = 4 * (size_t)blk * sizeof(F);
-    auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);
+    auto kern = aff_kernel<F>(p.aff_K, p.aff_minb, blk);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)blk, smem);
     if (occ < 1) occ = 1;
@@ -111,6 +114,7 @@ size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
 template <class F>
 size_t GroupOps<F>::curve_bytes_xyzz(const MsmPlan& p) {
     return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + 2 * ws_need((size_t)p.g.H * p.nblk, sizeof(XYZZ<F>)) +
+           2 * ws_need((size_t)p.g.H * (p.nblk / BMPC_FOLD_GROUP + 1), sizeof(XYZZ<F>)) +
            ws_need(p.g.H, sizeof(XYZZ<F>)) + ws_need(64, 4) + 1024;
 }
 
@@ -121,9 +125,14 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     XYZZ<F>* partials = ws_take<XYZZ<F>>(ctx, p.max_tasks);
     XYZZ<F>* blk_V = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
     XYZZ<F>* blk_R = ws_take<XYZZ<F>>(ctx, (size_t)g.H * p.nblk);
+    // block results are folded in groups of BMPC_FOLD_GROUP before the final kernel when a set has
+    // more of them than the final kernel's one block takes (msm_fold_kernel)
+    const uint32_t groups = p.nblk > BMPC_FINAL_THREADS ? p.nblk / BMPC_FOLD_GROUP : 0;
+    XYZZ<F>* grp_V = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / BMPC_FOLD_GROUP + 1));
+    XYZZ<F>* grp_R = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / BMPC_FOLD_GROUP + 1));
     XYZZ<F>* win = ws_take<XYZZ<F>>(ctx, g.H);
     uint32_t* ticket = ws_take<uint32_t>(ctx, 64);
-    if (!partials || !blk_V || !blk_R || !win || !ticket) {
+    if (!partials || !blk_V || !blk_R || !grp_V || !grp_R || !win || !ticket) {
         ctx->err = "msm workspace carve failed (curve)";
         return BMPC_ERR_INVALID;
     }
@@ -137,7 +146,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
         }
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
         size_t smem = 4 * (size_t)p.aff_block * sizeof(F);
-        auto kern = aff_kernel<F>(p.aff_K, p.aff_minb);
+        auto kern = aff_kernel<F>(p.aff_K, p.aff_minb, p.aff_block);
         LAUNCH(ctx, kern, p.aff_blocks, p.aff_block, smem, st, pts, s.sorted, s.desc, s.ntasks, partials, scratch,
                p.aff_HA, p.aff_HB, p.aff_G, (uint32_t)p.aff_whole_waves);
     } else {
@@ -169,8 +178,18 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
         CK(cudaMemsetAsync(ticket, 0, 4, st));
         uint32_t m_log = p.s_log, rb = p.rblock;
         while (rb > 1) { m_log++; rb >>= 1; }
-        LAUNCH(ctx, msm_final_kernel<F>, g.H, BMPC_FINAL_THREADS, smem, st, (const XYZZ<F>*)blk_V, (const XYZZ<F>*)blk_R,
-               g.H, p.nblk, m_log, g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        const XYZZ<F>*fin_V = blk_V, *fin_R = blk_R;
+        uint32_t fin_n = p.nblk;
+        if (groups) {
+            size_t fsmem = (size_t)BMPC_FOLD_GROUP * sizeof(XYZZ<F>);
+            dim3 fgrid(groups, g.H);
+            LAUNCH(ctx, msm_fold_kernel<F>, fgrid, BMPC_FOLD_GROUP, fsmem, st, (const XYZZ<F>*)blk_V,
+                   (const XYZZ<F>*)blk_R, p.nblk, m_log, grp_V, grp_R);
+            for (uint32_t q = BMPC_FOLD_GROUP; q > 1; q >>= 1) m_log++;
+            fin_V = grp_V; fin_R = grp_R; fin_n = groups;
+        }
+        LAUNCH(ctx, msm_final_kernel<F>, g.H, BMPC_FINAL_THREADS, smem, st, fin_V, fin_R,
+               g.H, fin_n, m_log, g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     }
     return BMPC_OK;
 }

@@ -207,6 +207,56 @@ msm_reduce_kernel(const XYZZ<F>* partials, const uint32_t* toff, uint32_t B, uin
     if (tid == 0) store_struct(blk_V + (size_t)w * gridDim.x + blockIdx.x, sm[0]);
 }
 
+// ---------------------------------------------------------------- 6b. fold of block results
+// The reduce kernel's suffix-scan step once more, over groups of `cnt` (power of two <= 256)
+// consecutive block results of one set: element e of a group weighs e * 2^m_log more than its
+// block-local weights say.  Emits one (V, R) pair per group; the final kernel then folds the groups
+// (its m_log grows by log2 cnt).  Why a separate launch: one 256-thread block folding 256 results
+// keeps 8 warps on ONE SM's multiplier pipe (0.7 ms measured); groups of 32 run as single warps on
+// different SMs, where a product costs its latency only, and let the reduce kernel itself use
+// small blocks (its scan levels, with every resident warp busy, are the expensive ones).
+// grid = (groups, sets), blockDim = cnt, smem = cnt * sizeof(XYZZ).
+template <class F>
+__global__ void __launch_bounds__(256)
+msm_fold_kernel(const XYZZ<F>* in_V, const XYZZ<F>* in_R, uint32_t n_in, uint32_t m_log,
+                XYZZ<F>* out_V, XYZZ<F>* out_R) {
+    extern __shared__ uint4 fold_smem[];
+    XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(fold_smem);
+    const uint32_t h = blockIdx.y, tid = threadIdx.x, cnt = blockDim.x;
+    const size_t e = (size_t)h * n_in + (size_t)blockIdx.x * cnt + tid;
+    XYZZ<F> run = load_struct(in_R + e), acc = load_struct(in_V + e);
+    sm[tid] = run;
+    __syncthreads();
+    for (uint32_t d = 1; d < cnt; d <<= 1) {
+        const bool has = tid + d < cnt;
+        XYZZ<F> t = XYZZ<F>::identity();
+        if (has) t = sm[tid + d];
+        __syncthreads();
+        if (has) {
+            run.add(t);
+            sm[tid] = run;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_struct(out_R + (size_t)h * gridDim.x + blockIdx.x, run);
+    if (tid >= 1) {
+        for (uint32_t q = 0; q < m_log; q++) run = run.dbl();
+        acc.add(run);
+    }
+    __syncthreads();
+    sm[tid] = acc;
+    __syncthreads();
+    for (uint32_t st = cnt >> 1; st > 0; st >>= 1) {
+        if (tid < st) {
+            XYZZ<F> x = sm[tid], y = sm[tid + st];
+            x.add(y);
+            sm[tid] = x;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_struct(out_V + (size_t)h * gridDim.x + blockIdx.x, sm[0]);
+}
+
 // ------------------------------------------------------------------------ 7. final
 // One block per bucket set: the same suffix-scan step over the set's nblk (<= 256, power of two)
 // block results -- block b's buckets weigh b * 2^m_log more (m_log = log2(rblock S)) -- then the

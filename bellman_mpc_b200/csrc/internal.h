@@ -215,6 +215,9 @@ enum { MSM_FLAG_EOF = 1, MSM_FLAG_IDENT_ANY = 2, MSM_FLAG_IDENT_TOP = 4 };
 // through the heavy-bucket combine first (which leaves the total in the first slot)
 #define BMPC_INLINE_PARTIALS 4u
 
+// msm_fold_kernel: block results of the bucket reduction are folded in groups of this many before
+// the final kernel; a set may have up to BMPC_FOLD_GROUP * 256 reduce blocks
+#define BMPC_FOLD_GROUP 32u
 struct MsmGeom {
     uint32_t c;        // window bits
     uint32_t W;        // number of windows = 255 / c + 1
@@ -231,7 +234,7 @@ struct MsmPlan {
     uint32_t nb;  // total buckets
     size_t max_pairs, max_tasks;
     // weighted-sum (bucket reduction) geometry per bucket set: each thread owns 2^s_log consecutive
-    // buckets, tpw = B >> s_log threads per set in nblk (<= 256) blocks of rblock (<= 128) threads
+    // buckets, tpw = B >> s_log threads per set in nblk (<= 8192) blocks of rblock (<= 256) threads
     uint32_t s_log, tpw, rblock, nblk;
     // batched-affine accumulation (msm_affine.cuh): decided per group in GroupOps::plan_affine
     bool affine = false, aff_whole_waves = false;

@@ -332,8 +332,8 @@ struct BlockCoop {
 // scratch holds T x G x (HA + HB) points.  G (slices per job) is chosen by the host so that the
 // grid is full: big MSMs run G = BMPC_AFF_G, small ones trade amortisation for parallelism.
 // Dynamic shared memory: 4 * blockDim.x * sizeof(F).  K = additions per inversion per thread.
-template <class F, int K, int MINB>
-__global__ void __launch_bounds__(BMPC_AFF_BLOCK, MINB)
+template <class F, int K, int MINB, int BLK = BMPC_AFF_BLOCK>
+__global__ void __launch_bounds__(BLK, MINB)
 msm_accumulate_affine_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint4* desc,
                              const uint32_t* ntasks_p, XYZZ<F>* partials, Affine<F>* scratch, uint32_t HA,
                              uint32_t HB, uint32_t G, uint32_t whole_waves) {

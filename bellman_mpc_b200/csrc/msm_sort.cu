@@ -114,10 +114,22 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 2 : 1) * 256;
         uint32_t s_log = 0;
         while (s_log < g.c - 1 && (((size_t)g.H * g.B) >> s_log) > capacity) s_log++;
-        while (s_log < g.c - 1 && (g.B >> s_log) > 256u * 256u) s_log++;
+        // Threads per reduce block.  The block's suffix scan and tree cost log2(rblock) additions each
+        // with every resident warp busy; the same levels cost a product's latency only in
+        // msm_fold_kernel (single warps spread over the SMs), so the blocks are kept small and the
+        // fold + final kernels take the upper levels.  BMPC_REDUCE_BLOCK: tuning knob.
+        // G2 keeps 256-thread blocks and no fold: its additions are three times as deep, the final
+        // kernel is latency-bound either way, and the extra fold levels and doublings cost more than
+        // the smaller blocks save (measured per G2 multiexp of the 2^22 proof: 4.19 -> 4.70 ms).
+        uint32_t rb = bases->group == BMPC_G1 ? 32 : 256;   // measured (G1, 2^19 buckets): 32 -> 2.38 ms, 64 -> 2.47, 128 -> 2.50, 256 -> 2.58 for combine + reduce + fold + final
+        if (getenv("BMPC_REDUCE_BLOCK")) {
+            uint32_t v = (uint32_t)atoi(getenv("BMPC_REDUCE_BLOCK"));
+            if (v == 32 || v == 64 || v == 128 || v == 256) rb = v;
+        }
+        while (s_log < g.c - 1 && (g.B >> s_log) > rb * BMPC_FOLD_GROUP * 256u) s_log++;
         p.s_log = s_log;
         p.tpw = g.B >> s_log;
-        p.rblock = p.tpw < 256 ? p.tpw : 256;
+        p.rblock = p.tpw < rb ? p.tpw : rb;
         p.nblk = p.tpw / p.rblock;
     }
     size_t b = 0;

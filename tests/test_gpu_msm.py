@@ -299,3 +299,47 @@ def test_hot_buckets_large(worker, tables, log_n):
     got = bm.multiexp(worker, (bases, 0), bm.FullDensity(), sc).wait()
     assert got == cref.g1_generator_mul(cref.fr_dot(ks, sc))
     bases.free()
+
+
+def test_list_mul_matrix(worker):
+    """mpc.rs:416-457: rows of a sparse matrix times a point list, G1 and G2 in one call; the
+    reference stops at the first empty row and leaves the rest of the result at the identity"""
+    from oracle import mpc as ompc
+    rng = random.Random(77)
+    n = 70
+    ks = rand_scalars(n, 71)
+    ks[5] = 0                                        # an identity element in the list
+    b1, b2 = known_dlog_bases(worker, bm.G1, ks), known_dlog_bases(worker, bm.G2, ks)
+    matrix = []
+    for i in range(64):
+        k = 0 if i == 50 else rng.randrange(1, 6)
+        matrix.append([(rng.choice([0, 1, 2, Q - 1, rng.randrange(Q), rng.randrange(1 << 40)]), rng.randrange(n))
+                       for _ in range(k)])
+    matrix[3] = [(rng.randrange(Q), 5), (0, 7)]      # a row summing to the identity
+    matrix[4] = [(7, 9), (Q - 7, 9)]                 # P - P
+    matrix[6] = [(rng.randrange(Q), 11)] * 2         # the same entry twice (doubling inside the row)
+    r1, r2 = bm.list_mul_matrix(b1, b2, matrix)
+    assert len(r1) == n and len(r2) == n
+    for G, got in ((curves.G1, r1.read()), (curves.G2, r2.read())):
+        want = b""
+        for i in range(n):
+            dot = sum(cf * ks[idx] for cf, idx in matrix[i]) % Q if i < 50 else 0
+            want += G.to_uncompressed(G.mul(G.gen, dot))
+        assert got == want
+    # the restatement of the reference on the same inputs (small case: big-integer curve arithmetic)
+    G = curves.G1
+    lst = [G.mul(G.gen, k) for k in ks[:12]]
+    small = [[(cf, idx % 12) for cf, idx in row] for row in matrix[:8]]
+    s1 = bm.Bases.from_uncompressed(worker, bm.G1, b"".join(G.to_uncompressed(p) for p in lst))
+    s2 = known_dlog_bases(worker, bm.G2, ks[:12])
+    o1, o2 = bm.list_mul_matrix(s1, s2, small)
+    assert o1.read() == b"".join(G.to_uncompressed(p) for p in ompc.list_mul_matrix(G, lst, small))
+    # empty matrix -> all identity; index panics of the reference -> AssertionError
+    e1, e2 = bm.list_mul_matrix(s1, s2, [])
+    assert e1.read() == G.to_uncompressed(None) * 12
+    with pytest.raises(AssertionError):
+        bm.list_mul_matrix(s1, s2, [[(1, 12)]])
+    with pytest.raises(AssertionError):
+        bm.list_mul_matrix(s1, s2, [[(1, 0)]] * 13)
+    for b in (b1, b2, r1, r2, s1, s2, o1, o2, e1, e2):
+        b.free()
