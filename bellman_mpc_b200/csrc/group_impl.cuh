@@ -16,7 +16,10 @@ template <class F>
 static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb, uint32_t blk = 128) {
     // 256-thread blocks (BMPC_AFF_BLOCKDIM=256, experiment): half as many block inversions per SM,
     // two resident blocks instead of four
-    if (blk == 256) return msm_accumulate_affine_kernel<F, 384, 2, 256>;
+    if constexpr (sizeof(F) == sizeof(Fp)) {
+        if (blk == 512) return msm_accumulate_affine_kernel<F, 384, 1, 512>;
+        if (blk == 256) return msm_accumulate_affine_kernel<F, 384, 2, 256>;
+    }
     if (K == 384) {
         if (minb == 4) return msm_accumulate_affine_kernel<F, 384, 4>;
         if (minb == 3) return msm_accumulate_affine_kernel<F, 384, 3>;
@@ -37,10 +40,14 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     int sms = 148, occ = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     // tuning knobs: threads per block (power of two <= 128), additions per inversion (128 | 384)
-    uint32_t blk = 128;
+    // G1: 256-thread blocks (two per SM) halve the block inversions of four 128-thread blocks: 2^24
+    // 59.78 -> 58.36 ms, 2^21 9.04 -> 8.97 ms, create_proof 2^22 0.1263 -> 0.1231 s; one 512-thread
+    // block per SM pays only for the largest bucket sets (2^24: 57.86 ms, but 2^21: 9.43 ms).
+    // G2 stays at 128 (168 registers, 3 blocks per SM).
+    uint32_t blk = sizeof(F) == sizeof(Fp) ? (p.nb >= (1u << 21) ? 512 : 256) : 128;
     if (getenv("BMPC_AFF_BLOCKDIM")) {
         uint32_t v = (uint32_t)atoi(getenv("BMPC_AFF_BLOCKDIM"));
-        if (v == 32 || v == 64 || v == 128 || v == 256) blk = v;
+        if (v == 32 || v == 64 || v == 128 || ((v == 256 || v == 512) && sizeof(F) == sizeof(Fp))) blk = v;
     }
     // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
     // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 at 2^22: 168 registers (3 blocks per
