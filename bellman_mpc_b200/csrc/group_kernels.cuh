@@ -83,6 +83,7 @@ msm_accumulate_kernel(const Affine<F>* bases, const uint32_t* sorted, const uint
 // bucket's partial sums.  Typical heavy buckets hold 2..30 partials (the over-full low buckets of
 // the top window); 0/1-heavy witnesses produce a few buckets with thousands, which the 128
 // threads fold in strides before the shared-memory tree.
+#define BMPC_HEAVY_WARP_MAX 64u
 template <class F>
 __global__ void __launch_bounds__(128)
 msm_combine_heavy_kernel(const uint32_t* toff, const uint32_t* heavy_list,
@@ -90,10 +91,49 @@ msm_combine_heavy_kernel(const uint32_t* toff, const uint32_t* heavy_list,
     extern __shared__ uint4 heavy_smem[];
     XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(heavy_smem);
     const uint32_t nh = *heavy_count;
+    // Pass 1, one WARP per bucket: buckets with a few dozen partial sums (with window tables the low
+    // 2^12 buckets, which the short top window fills a second time: ~21 slices each at 2^24).  A
+    // 128-thread block per bucket left three of its four warps idle in the tree: 1.2 ms for 4096
+    // buckets.  Buckets with more than BMPC_HEAVY_WARP_MAX partial sums wait for pass 2.
+    {
+        const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+        XYZZ<F>* wsm = sm + 32u * wib;
+        const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+        for (uint32_t h = blockIdx.x * (blockDim.x >> 5) + wib; h < nh; h += nwarps) {
+            uint32_t b = heavy_list[h];
+            uint32_t t0 = toff[b], t1 = toff[b + 1];
+            uint32_t k = t1 - t0;
+            if (k > BMPC_HEAVY_WARP_MAX) continue;
+            uint32_t width = 1;                  // power of two >= min(k, 32)
+            while (width < k && width < 32u) width <<= 1;
+            if (lane < width) {
+                XYZZ<F> acc = XYZZ<F>::identity();
+                for (uint32_t t = t0 + lane; t < t1; t += 32u) {
+                    XYZZ<F> v = load_struct(partials + t);
+                    acc.add(v);
+                }
+                wsm[lane] = acc;
+            }
+            __syncwarp();
+            for (uint32_t st = width >> 1; st > 0; st >>= 1) {
+                if (lane < st) {
+                    XYZZ<F> x = wsm[lane], y = wsm[lane + st];
+                    x.add(y);
+                    wsm[lane] = x;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) store_struct(partials + t0, wsm[0]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // Pass 2, one BLOCK per bucket: the few buckets with hundreds or thousands of partial sums.
     for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
         uint32_t b = heavy_list[h];
         uint32_t t0 = toff[b], t1 = toff[b + 1];
         uint32_t k = t1 - t0;
+        if (k <= BMPC_HEAVY_WARP_MAX) continue;   // block-uniform: done in pass 1
         uint32_t width = 1;                      // power of two >= min(k, 128)
         while (width < k && width < 128u) width <<= 1;
         if (threadIdx.x < width) {
