@@ -84,6 +84,14 @@ public:
         check(bmpc_fixed_base_mul(w.ctx(), group, base, k.empty() ? nullptr : k[0].data(), k.size(), 0, &h), w.ctx());
         return std::make_shared<Bases>(w, h);
     }
+    // mpc.rs:647-706 make_new_paramter / make_new_tau_paramter: element i times k[i], or every
+    // element times k[0] (per_element = false)
+    std::shared_ptr<Bases> scalar_mul(const std::vector<Scalar>& k, bool per_element = true) const {
+        bmpc_bases* h = nullptr;
+        if (k.empty() || (per_element && k.size() != len())) throw std::logic_error("length mismatch");
+        check(bmpc_batch_scalar_mul(w_->ctx(), h_, k[0].data(), per_element ? 1 : 0, &h), w_->ctx());
+        return std::make_shared<Bases>(*w_, h);
+    }
     void precompute(int window_bits = 0) { check(bmpc_bases_precompute(w_->ctx(), h_, window_bits), w_->ctx()); }
     size_t len() const { return bmpc_bases_len(h_); }
     int group() const { return bmpc_bases_group(h_); }
@@ -98,6 +106,30 @@ private:
     bmpc_bases* h_ = nullptr;
 };
 using Source = std::pair<std::shared_ptr<Bases>, size_t>;
+
+// ---- list_mul_matrix (groth16/mpc.rs:416-457) -------------------------------------------------
+// result[i] = sum_j list[matrix[i][j].second] * matrix[i][j].first for the rows before the first
+// empty one (the reference `break`s there), identity elsewhere; both results have the lists' length.
+// Coefficients canonical.  An index out of range panics in the reference: std::logic_error here.
+using SparseMatrix = std::vector<std::vector<std::pair<Scalar, size_t>>>;
+inline std::pair<std::shared_ptr<Bases>, std::shared_ptr<Bases>>
+list_mul_matrix(const Worker& w, const Bases& list_g1, const Bases& list_g2, const SparseMatrix& matrix) {
+    std::vector<uint64_t> row_ptr(matrix.size() + 1, 0), coeffs;
+    std::vector<uint32_t> cols;
+    for (size_t i = 0; i < matrix.size(); i++) {
+        row_ptr[i + 1] = row_ptr[i] + matrix[i].size();
+        for (const auto& e : matrix[i]) {
+            if (e.second > 0xffffffffull) throw std::logic_error("index out of bounds");
+            cols.push_back((uint32_t)e.second);
+            coeffs.insert(coeffs.end(), e.first.begin(), e.first.end());
+        }
+    }
+    bmpc_bases *h1 = nullptr, *h2 = nullptr;
+    check(bmpc_list_mul_matrix(w.ctx(), list_g1.handle(), row_ptr.data(), cols.data(), coeffs.data(), matrix.size(), &h1), w.ctx());
+    auto r1 = std::make_shared<Bases>(w, h1);
+    check(bmpc_list_mul_matrix(w.ctx(), list_g2.handle(), row_ptr.data(), cols.data(), coeffs.data(), matrix.size(), &h2), w.ctx());
+    return {r1, std::make_shared<Bases>(w, h2)};
+}
 
 // ---- QueryDensity (multiexp.rs:88-157) --------------------------------------------------------
 struct FullDensity {

@@ -71,6 +71,42 @@ int main() {
     try { multiexp(worker, Source{bases, 5}, FullDensity{}, s).wait(); } catch (const UnexpectedEof&) { threw = true; }
     REQUIRE(threw);
 
+    // ---- list_mul_matrix (mpc.rs:416-457) and per-element scalar multiplication (:647-706):
+    // row i = sum_j m_ij * (k_idx G) == (sum_j m_ij k_idx) G; rows after the first empty one stay O
+    {
+        const size_t ln = 24;
+        std::vector<Scalar> lk(k.begin(), k.begin() + ln);
+        auto l1 = Bases::fixed_base_mul(worker, BMPC_G1, gen.data(), lk);
+        SparseMatrix m(10);
+        std::vector<Scalar> rowdot(ln, Scalar{0, 0, 0, 0});
+        for (size_t i = 0; i < m.size(); i++) {
+            if (i == 7) continue;                                   // the reference stops here
+            unsigned __int128 acc = 0;
+            for (size_t j = 0; j < 1 + i % 4; j++) {
+                uint64_t cf = rng() >> 34;
+                size_t idx = rng() % ln;
+                m[i].push_back({Scalar{cf, 0, 0, 0}, idx});
+                acc += (unsigned __int128)cf * lk[idx][0];
+            }
+            if (i < 7) rowdot[i] = {(uint64_t)acc, (uint64_t)(acc >> 64), 0, 0};
+        }
+        auto res = list_mul_matrix(worker, *l1, *l1, m);           // the same G1 list in both slots
+        auto want = Bases::fixed_base_mul(worker, BMPC_G1, gen.data(), rowdot)->read(0, ln);
+        REQUIRE(res.first->len() == ln && res.first->read(0, ln) == want);
+        REQUIRE(res.second->read(0, ln) == want);
+        bool oob = false;
+        try { list_mul_matrix(worker, *l1, *l1, SparseMatrix{{{Scalar{1, 0, 0, 0}, ln}}}); } catch (const std::logic_error&) { oob = true; }
+        REQUIRE(oob);
+        std::vector<Scalar> mult(ln), prod(ln);
+        for (size_t i = 0; i < ln; i++) {
+            uint64_t mi = rng() >> 34;
+            unsigned __int128 pr = (unsigned __int128)mi * lk[i][0];
+            mult[i] = {mi, 0, 0, 0};
+            prod[i] = {(uint64_t)pr, (uint64_t)(pr >> 64), 0, 0};
+        }
+        REQUIRE(l1->scalar_mul(mult)->read(0, ln) == Bases::fixed_base_mul(worker, BMPC_G1, gen.data(), prod)->read(0, ln));
+    }
+
     // ---- fft_composition (domain.rs:427-463)
     for (unsigned logn = 0; logn < 11; logn++) {
         std::vector<Scalar> c(size_t(1) << logn);
