@@ -302,7 +302,7 @@ def run_ours(args):
         "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": (bytes_per_point * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
         "traffic": peaks.get("acc_traffic_bytes") if (world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute) else None,
-        "traffic_source": "profiles/r01_ncu_kernel_summaries.json (ncu --set full, same command, 1 GPU, 2^24)",
+        "traffic_source": "profiles/r01_ncu_kernel_summaries.json (ncu --set full, same command, 1 GPU, 2^24; affine kernel: r01d capture)",
         "algorithmic_bytes": bytes_per_point * n,
         "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
         "kernel_ms": acc_ms, "share_of_step": acc_ms / ms if ms else None,
