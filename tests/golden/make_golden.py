@@ -65,5 +65,22 @@ for a, b in ((False, False), (True, False)):
                          "b_aux_density": [int(x) for x in pr.b_aux_density.bv],
                          "proof": proof.to_bytes(E).hex()})
 out["crs_xordemo"] = crs
+
+# list_mul_matrix (mpc.rs:416-457): own generator so that the vectors above keep their values
+from oracle import mpc as ompc  # noqa: E402
+rng2 = random.Random(4160457)
+out["list_mul_matrix"] = []
+for gname, G, n in (("G1", curves.G1, 9), ("G2", curves.G2, 5)):
+    lst = [G.mul(G.gen, rng2.randrange(1, Q)) for _ in range(n)]
+    lst[1] = G.identity()
+    matrix = []
+    for i in range(n - 1):
+        k = 0 if i == n - 3 else rng2.randrange(1, 4)         # an empty row: the reference stops there
+        matrix.append([(rng2.choice([0, 1, Q - 1, rng2.randrange(Q), rng2.randrange(1 << 40)]), rng2.randrange(n))
+                       for _ in range(k)])
+    res = ompc.list_mul_matrix(G, lst, matrix)
+    out["list_mul_matrix"].append({"group": gname, "list": "".join(G.to_uncompressed(p).hex() for p in lst),
+                                   "matrix": [[[hex(cf), idx] for cf, idx in row] for row in matrix],
+                                   "result": "".join(G.to_uncompressed(p).hex() for p in res)})
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "vectors.json"), "w"), indent=0)
 print("wrote vectors.json")
