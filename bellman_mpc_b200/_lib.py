@@ -23,7 +23,8 @@ EXPORTS = [
     "bmpc_ctx_launch_count", "bmpc_ctx_profile", "bmpc_ctx_profile_read",
     "bmpc_bases_register", "bmpc_bases_register_dev", "bmpc_bases_precompute", "bmpc_bases_len", "bmpc_bases_group",
     "bmpc_bases_read", "bmpc_bases_dev_ptr", "bmpc_bases_free",
-    "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_sum_partials",
+    "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_multiexp_shard_dev",
+    "bmpc_msm_flags_status", "bmpc_sum_partials",
     "bmpc_partial_bytes", "bmpc_msm_geometry", "bmpc_msm_accumulate_info",
     "bmpc_domain_from_coeffs", "bmpc_domain_from_coeffs_dev", "bmpc_domain_len", "bmpc_domain_exp",
     "bmpc_domain_into_coeffs", "bmpc_domain_dev_ptr", "bmpc_domain_free", "bmpc_domain_transform",
@@ -60,7 +61,8 @@ PROOF_PARTIAL_BYTES = 1920      # BMPC_PROOF_PARTIAL_BYTES: 6 G1 XYZZ (192 B) + 
 
 class ProofShard(C.Structure):
     """bmpc_proof_shard"""
-    _fields_ = [("base_offset", C.c_size_t * 8), ("h_lo", C.c_size_t), ("h_hi", C.c_size_t)]
+    _fields_ = [("base_offset", C.c_size_t * 8), ("h_lo", C.c_size_t), ("h_hi", C.c_size_t),
+                ("n_total", C.c_size_t * 8)]
 
 
 class Csr(C.Structure):
@@ -107,6 +109,8 @@ def load():
         "bmpc_multiexp": (i32, [vp, vp, sz, vp, sz, vp, sz, vp]),
         "bmpc_multiexp_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
         "bmpc_multiexp_partial_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
+        "bmpc_multiexp_shard_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, sz, vp, C.POINTER(u32), vp]),
+        "bmpc_msm_flags_status": (i32, [u32]),
         "bmpc_sum_partials": (i32, [vp, i32, vp, sz, vp, vp]),
         "bmpc_partial_bytes": (sz, [i32]),
         "bmpc_msm_geometry": (i32, [vp, vp, sz, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
@@ -135,7 +139,7 @@ def load():
         "bmpc_fr_to_canonical_dev": (i32, [vp, vp, sz, vp]),
         "bmpc_create_proof": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), vp, vp, vp]),
         "bmpc_create_proof_partials": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), C.POINTER(ProofShard), vp,
-                                             C.POINTER(i32 * 8)]),
+                                             C.POINTER(u32 * 8)]),
         "bmpc_create_proof_finish": (i32, [vp, C.POINTER(Params), vp, sz, vp, vp, vp]),
         "bmpc_batch_scalar_mul": (i32, [vp, vp, vp, i32, C.POINTER(vp)]),
         "bmpc_fixed_base_mul": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),

@@ -37,9 +37,12 @@ struct MsmPending {
     uint8_t* out = nullptr;
 };
 
+// n_ref: the length of the WHOLE exponent vector when this call is one shard of it (the reference
+// derives its window size -- and with it which error wins -- from that length, multiexp.rs:267-271);
+// 0 = this call is the whole multiexp.
 int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* d_scalars,
                      size_t n, const uint64_t* d_density, size_t density_len, uint8_t* out, void* d_partial,
-                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend) {
+                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend, size_t n_ref = 0) {
     *pend = MsmPending();
     if (!bases || (!out && !d_partial)) return BMPC_ERR_INVALID;
     if (d_density && density_len != n) return BMPC_ERR_LENGTH_MISMATCH;  // multiexp.rs:273-278
@@ -55,7 +58,13 @@ int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
     uint32_t* d_flags = reinterpret_cast<uint32_t*>(ctx->d_stage);
     uint8_t* d_bytes = ctx->d_stage + 64;
     int mode = d_partial ? 1 : 0;
-    MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr);
+    MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr, n_ref);
+    // histogram, offsets, cursors and task descriptors are 32-bit over the n * W (position, window)
+    // pairs: refuse what would overflow them instead of corrupting the sort
+    if (p.max_pairs >= ((size_t)1 << 32) - 1) {
+        ctx->err = "multiexp too large for one call: n * windows >= 2^32 (split the exponent range)";
+        return BMPC_ERR_INVALID;
+    }
     if (bases->group == BMPC_G1) GroupOps<Fp>::plan_affine(ctx, p);
     else GroupOps<Fp2>::plan_affine(ctx, p);
     size_t curve_bytes = bases->group == BMPC_G1 ? GroupOps<Fp>::curve_bytes(p) : GroupOps<Fp2>::curve_bytes(p);
@@ -79,9 +88,11 @@ int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
 }
 
 // after the stream was synchronised
-int multiexp_collect(const MsmPending& pend) {
+int multiexp_collect(const MsmPending& pend, uint32_t* flags_out = nullptr) {
+    if (flags_out) *flags_out = 0;
     if (!pend.st) return BMPC_OK;
     uint32_t flags = *reinterpret_cast<const uint32_t*>(pend.h);
+    if (flags_out) *flags_out = flags;
     int status = flags_to_status(flags);
     if (status == BMPC_OK && pend.out) memcpy(pend.out, pend.h + 64, pend.out_bytes);
     return status;
@@ -89,14 +100,30 @@ int multiexp_collect(const MsmPending& pend) {
 
 int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
                         const uint64_t* d_scalars, size_t n, const uint64_t* d_density,
-                        size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st) {
+                        size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st,
+                        size_t n_ref = 0, uint32_t* flags_out = nullptr) {
     MsmPending pend;
     int rc = multiexp_enqueue(ctx, bases, base_offset, d_scalars, n, d_density, density_len, out, d_partial, st,
-                              ctx->h_stage, &pend);
+                              ctx->h_stage, &pend, n_ref);
     if (rc) return rc;
     if (pend.st) CK(cudaStreamSynchronize(st));
-    return multiexp_collect(pend);
+    return multiexp_collect(pend, flags_out);
 }
+
+// a bmpc_bases under construction: device memory and the handle are released unless handed out
+struct BasesGuard {
+    bmpc_ctx* ctx;
+    bmpc_bases* b = nullptr;
+    explicit BasesGuard(bmpc_ctx* c) : ctx(c) {}
+    bmpc_bases* release() { bmpc_bases* r = b; b = nullptr; return r; }
+    ~BasesGuard() {
+        if (!b) return;
+        cudaStreamSynchronize(ctx->own_stream);
+        if (b->d_points) cudaFree(b->d_points);
+        if (b->d_inf) cudaFree(b->d_inf);
+        delete b;
+    }
+};
 
 int register_points(bmpc_ctx* ctx, bmpc_bases* b, cudaStream_t st) {
     size_t nw = (b->n + 31) / 32 + 1;
@@ -148,6 +175,8 @@ void bmpc_ctx_destroy(bmpc_ctx* ctx) {
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->last_done) cudaEventDestroy(ctx->last_done);
+    if (ctx->inputs_ready) cudaEventDestroy(ctx->inputs_ready);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -201,34 +230,32 @@ int bmpc_bases_register(bmpc_ctx* ctx, int group, const void* points, size_t n, 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t pb = group == BMPC_G1 ? 96 : 192;
     if (stride == 0) stride = pb;
     if (stride < pb) return BMPC_ERR_INVALID;
-    bmpc_bases* b = new bmpc_bases();
+    if (form != BMPC_FORM_MONT_XY && form != BMPC_FORM_UNCOMPRESSED_BE) return BMPC_ERR_INVALID;
+    BasesGuard bg(ctx);
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
+    DevBuf raw;
     if (n) {
         if (form == BMPC_FORM_MONT_XY) {
             CK(cudaMemcpy2DAsync(b->d_points, pb, points, stride, pb, n, cudaMemcpyHostToDevice, st));
-        } else if (form == BMPC_FORM_UNCOMPRESSED_BE) {
-            uint8_t* d_raw;
-            CK(cudaMalloc(&d_raw, n * stride));
-            CK(cudaMemcpyAsync(d_raw, points, n * stride, cudaMemcpyHostToDevice, st));
-            int rcd = group == BMPC_G1 ? GroupOps<Fp>::decode(ctx, d_raw, stride, n, b->d_points, st)
-                                       : GroupOps<Fp2>::decode(ctx, d_raw, stride, n, b->d_points, st);
-            if (rcd) return rcd;
-            CK(cudaStreamSynchronize(st));
-            CK(cudaFree(d_raw));
         } else {
-            delete b;
-            return BMPC_ERR_INVALID;
+            CK(cudaMalloc(&raw.p, n * stride));
+            CK(cudaMemcpyAsync(raw.p, points, n * stride, cudaMemcpyHostToDevice, st));
+            int rcd = group == BMPC_G1 ? GroupOps<Fp>::decode(ctx, raw.as<uint8_t>(), stride, n, b->d_points, st)
+                                       : GroupOps<Fp2>::decode(ctx, raw.as<uint8_t>(), stride, n, b->d_points, st);
+            if (rcd) return rcd;
         }
     }
     int rc = register_points(ctx, b, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
-    *out = b;
+    *out = bg.release();
     return BMPC_OK;
 }
 
@@ -238,8 +265,10 @@ int bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont,
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     size_t pb = group == BMPC_G1 ? 96 : 192;
-    bmpc_bases* b = new bmpc_bases();
+    BasesGuard bg(ctx);
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
@@ -247,7 +276,7 @@ int bmpc_bases_register_dev(bmpc_ctx* ctx, int group, const void* d_points_mont,
     int rc = register_points(ctx, b, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
-    *out = b;
+    *out = bg.release();
     return BMPC_OK;
 }
 
@@ -257,6 +286,7 @@ int bmpc_bases_precompute(bmpc_ctx* ctx, bmpc_bases* b, int window_bits) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     uint32_t c = window_bits > 0 ? (uint32_t)window_bits : msm_table_window(b->n);
     if (c < 2) c = 2;
     if (c > 22) c = 22;
@@ -287,16 +317,17 @@ int bmpc_bases_read(bmpc_ctx* ctx, const bmpc_bases* b, size_t start, size_t cou
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t pb = b->group == BMPC_G1 ? 96 : 192;
-    uint8_t* d_out;
-    CK(cudaMalloc(&d_out, count * pb));
+    DevBuf obuf;
+    CK(cudaMalloc(&obuf.p, count * pb));
+    uint8_t* d_out = obuf.as<uint8_t>();
     int rce = b->group == BMPC_G1
                   ? GroupOps<Fp>::encode(ctx, (const G1Affine*)b->d_points + start, count, d_out, st)
                   : GroupOps<Fp2>::encode(ctx, (const G2Affine*)b->d_points + start, count, d_out, st);
     if (rce) return rce;
     CK(cudaMemcpyAsync(out, d_out, count * pb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d_out));
     return BMPC_OK;
 }
 
@@ -342,8 +373,10 @@ int bmpc_multiexp_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset
     if (!ctx || !out) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return multiexp_dev_locked(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len,
-                               out, nullptr, pick_stream(ctx, stream));
+                               out, nullptr, st);
 }
 
 int bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
@@ -352,9 +385,28 @@ int bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t bas
     if (!ctx || !d_partial_out) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return multiexp_dev_locked(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len,
-                               nullptr, d_partial_out, pick_stream(ctx, stream));
+                               nullptr, d_partial_out, st);
 }
+
+int bmpc_multiexp_shard_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                            const uint64_t* d_scalars, size_t n, const uint64_t* d_density_words,
+                            size_t density_len, size_t n_total, void* d_partial_out, uint32_t* flags_out,
+                            void* stream) {
+    if (!ctx || !d_partial_out || !flags_out || n_total < n) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    int rc = multiexp_dev_locked(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len,
+                                 nullptr, d_partial_out, st, n_total, flags_out);
+    // the shard's own status is not the multiexp's: the caller ORs the flag words of all shards
+    return (rc == BMPC_ERR_UNEXPECTED_EOF || rc == BMPC_ERR_UNEXPECTED_IDENTITY) ? BMPC_OK : rc;
+}
+
+int bmpc_msm_flags_status(uint32_t flags_or) { return flags_to_status(flags_or); }
 
 int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* scalars,
                   size_t n, const uint64_t* density_words, size_t density_len, uint8_t* out) {
@@ -363,6 +415,7 @@ int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, co
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     uint64_t* d_s = nullptr;
     uint64_t* d_d = nullptr;
     size_t dw = (n + 63) / 64;
@@ -386,6 +439,7 @@ int bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t c
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     size_t ob = group == BMPC_G1 ? 96 : 192;
     uint8_t* d_bytes = ctx->d_stage + 64;
     int rcs = group == BMPC_G1 ? GroupOps<Fp>::sum_partials(ctx, d_partials, (uint32_t)count, d_bytes, st)
@@ -420,6 +474,7 @@ int bmpc_domain_from_coeffs(bmpc_ctx* ctx, const uint64_t* coeffs, size_t len, b
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     bmpc_domain* d;
     int rc = domain_alloc(ctx, len, &d);
     if (rc) return rc;
@@ -436,6 +491,7 @@ int bmpc_domain_from_coeffs_dev(bmpc_ctx* ctx, const uint64_t* d_coeffs, size_t 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     bmpc_domain* d;
     int rc = domain_alloc(ctx, len, &d);
     if (rc) return rc;
@@ -453,6 +509,8 @@ int bmpc_domain_into_coeffs(bmpc_ctx* ctx, const bmpc_domain* d, uint64_t* out) 
     if (!ctx || !d || !out) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
+    // the domain may still be in flight on a caller's stream: wait for the context's last call
+    if (ctx->last_valid) CK(cudaEventSynchronize(ctx->last_done));
     CK(cudaStreamSynchronize(ctx->own_stream));
     CK(cudaMemcpy(out, d->d, d->m * 32, cudaMemcpyDeviceToHost));
     return BMPC_OK;
@@ -472,21 +530,27 @@ int bmpc_domain_transform(bmpc_ctx* ctx, bmpc_domain* d, int op, void* stream) {
     if (!ctx || !d) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return ntt_dev_locked(ctx, d->d, d->exp, op, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return ntt_dev_locked(ctx, d->d, d->exp, op, st);
 }
 
 int bmpc_ntt_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_m, int op, void* stream) {
     if (!ctx || !d_coeffs) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return ntt_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_m, op, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return ntt_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_m, op, st);
 }
 
 int bmpc_ntt_batch_dev(bmpc_ctx* ctx, uint64_t* d_coeffs, uint32_t log_n, uint32_t batch, int inverse, void* stream) {
     if (!ctx || !d_coeffs) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return ntt_batch_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_n, batch, inverse != 0, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return ntt_batch_dev_locked(ctx, reinterpret_cast<Fr*>(d_coeffs), log_n, batch, inverse != 0, st);
 }
 
 int bmpc_fr_swap01_dev(bmpc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint32_t d0, uint32_t d1, uint32_t d2,
@@ -494,7 +558,9 @@ int bmpc_fr_swap01_dev(bmpc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uin
     if (!ctx || !d_in || !d_out || d_in == d_out) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return fr_swap01(ctx, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), d0, d1, d2, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return fr_swap01(ctx, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), d0, d1, d2, st);
 }
 
 int bmpc_ntt_fourstep_twiddle_dev(bmpc_ctx* ctx, uint64_t* d, uint32_t rows, uint32_t cols, uint32_t row0,
@@ -503,7 +569,9 @@ int bmpc_ntt_fourstep_twiddle_dev(bmpc_ctx* ctx, uint64_t* d, uint32_t rows, uin
     if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return fr_fourstep_twiddle(ctx, reinterpret_cast<Fr*>(d), rows, cols, row0, log_m, inverse != 0, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return fr_fourstep_twiddle(ctx, reinterpret_cast<Fr*>(d), rows, cols, row0, log_m, inverse != 0, st);
 }
 
 int bmpc_fr_scale_pow_dev(bmpc_ctx* ctx, uint64_t* d, size_t n, uint32_t first, uint32_t log_m, int which,
@@ -512,7 +580,9 @@ int bmpc_fr_scale_pow_dev(bmpc_ctx* ctx, uint64_t* d, size_t n, uint32_t first, 
     if (log_m >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
-    return fr_scale_pow(ctx, reinterpret_cast<Fr*>(d), n, first, log_m, which, pick_stream(ctx, stream));
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    return fr_scale_pow(ctx, reinterpret_cast<Fr*>(d), n, first, log_m, which, st);
 }
 
 int bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op) {
@@ -521,9 +591,13 @@ int bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t m = (size_t)1 << log_m;
-    Fr* d;
-    CK(cudaMalloc(&d, m * sizeof(Fr)));
+    // staged through the context's grow-only device buffer: a prover calling fft() in a loop pays
+    // no cudaMalloc / cudaFree per call
+    int rr = io_reserve(ctx, m * sizeof(Fr));
+    if (rr) return rr;
+    Fr* d = reinterpret_cast<Fr*>(ctx->io);
     CK(cudaMemcpyAsync(d, coeffs, m * 32, cudaMemcpyHostToDevice, st));
     int rc = ntt_dev_locked(ctx, d, log_m, op, st);
     if (rc == BMPC_OK) {
@@ -531,7 +605,6 @@ int bmpc_ntt(bmpc_ctx* ctx, uint64_t* coeffs, uint32_t log_m, int op) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BMPC_ERR_CUDA; }
     }
-    cudaFree(d);
     return rc;
 }
 
@@ -540,6 +613,7 @@ int bmpc_domain_distribute_powers(bmpc_ctx* ctx, bmpc_domain* d, const uint64_t 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     Fr* d_g = reinterpret_cast<Fr*>(ctx->d_stage + 1024);
     CK(cudaMemcpyAsync(d_g, g, 32, cudaMemcpyHostToDevice, st));
     int rcd = fr_distribute_powers(ctx, d->d, d->m, d_g, st);
@@ -553,6 +627,7 @@ int bmpc_domain_z(bmpc_ctx* ctx, const bmpc_domain* d, const uint64_t tau[4], ui
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     Fr* d_t = reinterpret_cast<Fr*>(ctx->d_stage + 1024);
     CK(cudaMemcpyAsync(d_t, tau, 32, cudaMemcpyHostToDevice, st));
     int rcz = fr_eval_z(ctx, d_t, d->exp, d_t + 1, st);
@@ -567,6 +642,7 @@ int bmpc_domain_divide_by_z_on_coset(bmpc_ctx* ctx, bmpc_domain* d, void* stream
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return fr_scale_zinv(ctx, d->d, d->m, d->exp, st);
 }
 
@@ -576,6 +652,7 @@ int bmpc_domain_mul_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* oth
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return fr_pointwise(ctx, 0, d->d, other->d, d->m, st);
 }
 
@@ -585,6 +662,7 @@ int bmpc_domain_sub_assign(bmpc_ctx* ctx, bmpc_domain* d, const bmpc_domain* oth
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return fr_pointwise(ctx, 1, d->d, other->d, d->m, st);
 }
 
@@ -596,6 +674,7 @@ int bmpc_h_coefficients_dev(bmpc_ctx* ctx, uint64_t* d_a, uint64_t* d_b, uint64_
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     size_t m = (size_t)1 << log_m;
     int rc = ws_reserve(ctx, 2 * ws_need(m, sizeof(Fr)));
     if (rc) return rc;
@@ -610,6 +689,7 @@ int bmpc_h_coefficients(bmpc_ctx* ctx, const uint64_t* a, const uint64_t* b, con
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t m = 1;
     uint32_t exp = 0;
     while (m < len) {
@@ -642,6 +722,7 @@ int bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* st
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
     return fr_pointwise(ctx, 2, (Fr*)d_vals, nullptr, n, st);
 }
 
@@ -652,14 +733,15 @@ namespace {
 // proof) and bmpc_create_proof_partials (one rank's share of the multiexps: `S` is the rank's
 // SLICE of the assignment, shard->base_offset[j] the first base each multiexp consumes inside the
 // rank's slice of the query vector, [h_lo, h_hi) its share of the H coefficients; the XYZZ partial
-// sums go to partials_out, the per-multiexp statuses to statuses_out, no tail).
+// sums go to partials_out, the per-multiexp raw flag words to flags_out, no tail).
 int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
                         const uint64_t s[4], const bmpc_proof_shard* shard, uint8_t* proof_out,
-                        uint8_t* partials_out, int* statuses_out) {
+                        uint8_t* partials_out, uint32_t* flags_out) {
     if (!P->h || !P->l || !P->a || !P->b_g1 || !P->b_g2) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     const size_t nc = S->num_constraints, ni = S->num_inputs, na = S->num_aux;
     size_t m = 1;
     uint32_t exp = 0;
@@ -828,7 +910,8 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         }
         if (!rc)
             rc = multiexp_enqueue(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens, jobs[j].n,
-                                  nullptr, jobs[j].out, js, ctx->h_stage + 256 * j, &pend[j]);
+                                  nullptr, jobs[j].out, js, ctx->h_stage + 256 * j, &pend[j],
+                                  shard ? shard->n_total[j] : 0);
         if (sk) swap_slot(sk);
         if (rc != BMPC_OK) {      // argument / launch errors; the multiexp statuses come from the flags
             cleanup();
@@ -837,13 +920,14 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     }
     for (auto& sl : ctx->slots) CKP(cudaStreamSynchronize(sl.stream));
     CKP(cudaStreamSynchronize(st));
-    for (int j = 0; j < 8; j++) statuses[j] = multiexp_collect(pend[j]);
+    uint32_t flags[8];
+    for (int j = 0; j < 8; j++) statuses[j] = multiexp_collect(pend[j], &flags[j]);
     if (shard) {   // one rank's share: hand back the partial sums and statuses, the caller gathers them
         CKP(cudaMemcpyAsync(ctx->h_stage, part_g1, 2304, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
         memcpy(partials_out, ctx->h_stage, 6 * sizeof(G1XYZZ));
         memcpy(partials_out + 6 * sizeof(G1XYZZ), ctx->h_stage + 1536, 2 * sizeof(G2XYZZ));
-        for (int j = 0; j < 8; j++) statuses_out[j] = statuses[j];
+        for (int j = 0; j < 8; j++) flags_out[j] = flags[j];
         cleanup();
         return BMPC_OK;
     }
@@ -881,9 +965,9 @@ int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment
 
 int bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S,
                                const bmpc_proof_shard* shard, uint8_t partials_out[BMPC_PROOF_PARTIAL_BYTES],
-                               int statuses_out[8]) {
-    if (!ctx || !P || !S || !shard || !partials_out || !statuses_out) return BMPC_ERR_INVALID;
-    return create_proof_common(ctx, P, S, nullptr, nullptr, shard, nullptr, partials_out, statuses_out);
+                               uint32_t flags_out[8]) {
+    if (!ctx || !P || !S || !shard || !partials_out || !flags_out) return BMPC_ERR_INVALID;
+    return create_proof_common(ctx, P, S, nullptr, nullptr, shard, nullptr, partials_out, flags_out);
 }
 
 int bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* P, const uint8_t* partials_all, size_t world,
@@ -892,6 +976,7 @@ int bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* P, const uint8_t*
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     // subversion check first, as in the single-GPU path (prover.rs:309-313)
     if ((P->delta_g1[0] & 0x40) || (P->delta_g2[0] & 0x40)) return BMPC_ERR_UNEXPECTED_IDENTITY;
     const size_t need = align_up(world * BMPC_PROOF_PARTIAL_BYTES, 256) + 8192;
@@ -942,15 +1027,17 @@ int read_section(bmpc_ctx* ctx, int group, const uint8_t* data, size_t len, size
     const size_t pb = group == BMPC_G1 ? 96 : 192;
     size_t avail = (len - *pos) / pb;
     size_t n = count < avail ? count : avail;
-    bmpc_bases* b = new bmpc_bases();
+    BasesGuard bg(ctx);
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
     uint32_t* d_err = reinterpret_cast<uint32_t*>(ctx->d_stage + 1536);
     uint32_t h_err = 0xffffffffu;
+    DevBuf raw;
     if (n) {
-        uint8_t* d_raw;
-        CK(cudaMalloc(&d_raw, n * pb));
+        CK(cudaMalloc(&raw.p, n * pb));
+        uint8_t* d_raw = raw.as<uint8_t>();
         CK(cudaMemcpyAsync(d_raw, data + *pos, n * pb, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_err, &h_err, 4, cudaMemcpyHostToDevice, st));
         int rc = group == BMPC_G1
@@ -959,18 +1046,13 @@ int read_section(bmpc_ctx* ctx, int group, const uint8_t* data, size_t len, size
         if (rc) return rc;
         CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        CK(cudaFree(d_raw));
     }
     *pos += n * pb;
     if (h_err != 0xffffffffu) {
         ctx->err = (h_err & 3u) == 2u ? "point at infinity" : (group == BMPC_G1 ? "invalid G1" : "invalid G2");
-        bmpc_bases_free(ctx, b);
         return BMPC_ERR_INVALID_DATA;
     }
-    if (n < count) {
-        bmpc_bases_free(ctx, b);
-        return BMPC_ERR_UNEXPECTED_EOF;
-    }
+    if (n < count) return BMPC_ERR_UNEXPECTED_EOF;
     size_t nw = (n + 31) / 32 + 1;
     CK(cudaMalloc(&b->d_inf, nw * 4));
     CK(cudaMemsetAsync(b->d_inf, 0, nw * 4, st));
@@ -978,7 +1060,7 @@ int read_section(bmpc_ctx* ctx, int group, const uint8_t* data, size_t len, size
                               : GroupOps<Fp2>::inf_bitmap(ctx, b->d_points, n, b->d_inf, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
-    *out = b;
+    *out = bg.release();
     return BMPC_OK;
 }
 
@@ -1008,6 +1090,7 @@ int bmpc_params_read(bmpc_ctx* ctx, const uint8_t* data, size_t len, int checked
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     memset(out, 0, sizeof(*out));
     size_t pos = 0;
     // VerifyingKey::read (mod.rs:161-221): six points, always checked, identity allowed
@@ -1076,13 +1159,16 @@ int bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* s
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t n = in->n;
     size_t pb = in->group == BMPC_G1 ? 96 : 192;
     size_t ns = per_element ? n : 1;
-    uint32_t* d_s;
-    CK(cudaMalloc(&d_s, (ns ? ns : 1) * 32));
+    DevBuf sbuf;
+    BasesGuard bg(ctx);
+    CK(cudaMalloc(&sbuf.p, (ns ? ns : 1) * 32));
+    uint32_t* d_s = sbuf.as<uint32_t>();
     if (ns) CK(cudaMemcpyAsync(d_s, scalars, ns * 32, cudaMemcpyHostToDevice, st));
-    bmpc_bases* b = new bmpc_bases();
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = in->group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
@@ -1092,8 +1178,7 @@ int bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* s
     int rc = register_points(ctx, b, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d_s));
-    *out = b;
+    *out = bg.release();
     return BMPC_OK;
 }
 
@@ -1102,11 +1187,12 @@ int bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* 
                          const uint64_t* coeffs, size_t n_rows, bmpc_bases** out) {
     if (!ctx || !list || !row_ptr || !out) return BMPC_ERR_INVALID;
     const size_t n = list->n;
-    // result[i] for i < matrix.len() indexes a vector of list.len() elements (:428-429, :445):
-    // a matrix taller than the list panics in the reference, and so does a column >= list.len()
-    if (n_rows > n) return BMPC_ERR_LENGTH_MISMATCH;
     size_t live = 0;                                     // rows before the first empty one (:432-434)
     while (live < n_rows && row_ptr[live + 1] > row_ptr[live]) live++;
+    // result[i] indexes a vector of list.len() elements (:428-429, :445) for the rows the loop
+    // PROCESSES: the reference panics only if a live row index reaches list.len() -- a matrix taller
+    // than the list whose first empty row comes earlier is fine -- or on a live column >= list.len()
+    if (live > n) return BMPC_ERR_LENGTH_MISMATCH;
     const size_t j0 = row_ptr[0], nnz = row_ptr[live] - j0;
     if (nnz && (!cols || !coeffs)) return BMPC_ERR_INVALID;
     if (nnz >= ((size_t)1 << 32)) return BMPC_ERR_INVALID;
@@ -1117,17 +1203,20 @@ int bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     const size_t pb = list->group == BMPC_G1 ? 96 : 192;
-    uint32_t *d_rp, *d_col, *d_cf;
-    CK(cudaMalloc(&d_rp, (live + 1) * 4));
-    CK(cudaMalloc(&d_col, (nnz ? nnz : 1) * 4));
-    CK(cudaMalloc(&d_cf, (nnz ? nnz : 1) * 32));
+    DevBuf rp_buf, col_buf, cf_buf;       // freed on every exit path
+    BasesGuard bg(ctx);
+    CK(cudaMalloc(&rp_buf.p, (live + 1) * 4));
+    CK(cudaMalloc(&col_buf.p, (nnz ? nnz : 1) * 4));
+    CK(cudaMalloc(&cf_buf.p, (nnz ? nnz : 1) * 32));
+    uint32_t *d_rp = rp_buf.as<uint32_t>(), *d_col = col_buf.as<uint32_t>(), *d_cf = cf_buf.as<uint32_t>();
     CK(cudaMemcpyAsync(d_rp, rp.data(), (live + 1) * 4, cudaMemcpyHostToDevice, st));
     if (nnz) {
         CK(cudaMemcpyAsync(d_col, cols + j0, nnz * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_cf, coeffs + j0 * 4, nnz * 32, cudaMemcpyHostToDevice, st));
     }
-    bmpc_bases* b = new bmpc_bases();
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = list->group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
@@ -1137,9 +1226,8 @@ int bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* 
     if (rcb) return rcb;
     int rc = register_points(ctx, b, st);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d_rp)); CK(cudaFree(d_col)); CK(cudaFree(d_cf));
-    *out = b;
+    CK(cudaStreamSynchronize(st));          // the temporaries are in use until here
+    *out = bg.release();
     return BMPC_OK;
 }
 
@@ -1149,23 +1237,25 @@ int bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uin
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     size_t pb = group == BMPC_G1 ? 96 : 192;
     size_t xb = group == BMPC_G1 ? sizeof(G1XYZZ) : sizeof(G2XYZZ);
-    uint8_t* d_base_raw;
-    void* d_base;
-    void* d_table;
-    uint32_t* d_s = nullptr;
-    CK(cudaMalloc(&d_base_raw, pb));
-    CK(cudaMalloc(&d_base, pb));
-    CK(cudaMalloc(&d_table, 32 * 256 * xb));
+    DevBuf raw_buf, base_buf, table_buf, s_buf;
+    BasesGuard bg(ctx);
+    CK(cudaMalloc(&raw_buf.p, pb));
+    CK(cudaMalloc(&base_buf.p, pb));
+    CK(cudaMalloc(&table_buf.p, 32 * 256 * xb));
+    uint8_t* d_base_raw = raw_buf.as<uint8_t>();
+    void* d_base = base_buf.p;
+    void* d_table = table_buf.p;
     CK(cudaMemcpyAsync(d_base_raw, base, pb, cudaMemcpyHostToDevice, st));
     const uint32_t* sc = (const uint32_t*)scalars;
     if (!scalars_on_device && n) {
-        CK(cudaMalloc(&d_s, n * 32));
-        CK(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, st));
-        sc = d_s;
+        CK(cudaMalloc(&s_buf.p, n * 32));
+        CK(cudaMemcpyAsync(s_buf.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        sc = s_buf.as<uint32_t>();
     }
-    bmpc_bases* b = new bmpc_bases();
+    bmpc_bases* b = bg.b = new bmpc_bases();
     b->group = group;
     b->n = n;
     CK(cudaMalloc(&b->d_points, (n ? n : 1) * pb));
@@ -1181,9 +1271,7 @@ int bmpc_fixed_base_mul(bmpc_ctx* ctx, int group, const uint8_t* base, const uin
     int rc = register_points(ctx, b, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d_base_raw)); CK(cudaFree(d_base)); CK(cudaFree(d_table));
-    if (d_s) CK(cudaFree(d_s));
-    *out = b;
+    *out = bg.release();
     return BMPC_OK;
 }
 

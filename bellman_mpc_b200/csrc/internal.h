@@ -61,6 +61,13 @@ struct bmpc_ctx {
     };
     Slot slots[2];
     cudaEvent_t inputs_ready = nullptr;
+    // Stream contract: the scratch arena, the twiddle / power tables and the staging words are shared
+    // per context, so calls on DIFFERENT streams must not overlap.  Every stream-taking entry point
+    // opens a StreamScope: a call arriving on another stream than the previous one first waits (on
+    // the device) for an event recorded at the end of that previous call.
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t last_done = nullptr;
+    bool last_valid = false;
     // device staging for host-pointer entry points (scalars, density words); grow-only so that a
     // prover calling in a loop does not pay cudaMalloc/cudaFree per call
     char* io = nullptr;
@@ -132,6 +139,30 @@ struct DeviceGuard {
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
     }
+};
+
+// Orders a call on `st` after the context's previous call if that ran on another stream, and
+// publishes its own completion point on exit (see bmpc_ctx::last_done).
+struct StreamScope {
+    bmpc_ctx* ctx;
+    cudaStream_t st;
+    StreamScope(bmpc_ctx* c, cudaStream_t s) : ctx(c), st(s) {
+        if (!ctx->last_done) cudaEventCreateWithFlags(&ctx->last_done, cudaEventDisableTiming);
+        if (ctx->last_valid && ctx->last_stream != st) cudaStreamWaitEvent(st, ctx->last_done, 0);
+    }
+    ~StreamScope() {
+        if (ctx->last_done && cudaEventRecord(ctx->last_done, st) == cudaSuccess) {
+            ctx->last_stream = st;
+            ctx->last_valid = true;
+        }
+    }
+};
+
+// device / handle temporaries of the setup-time entry points: released on every exit path
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
 // RAII event pair around one kernel launch (only when profiling is on)
@@ -252,7 +283,7 @@ struct MsmSorted {      // outputs of the sort stage (device pointers into the a
     uint32_t* ntasks;   // device pointer to the task count (== toff[nb])
 };
 
-MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density);
+MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density, size_t n_ref = 0);
 uint32_t msm_table_window(size_t n_bases);  // window bits used for precomputed tables
 // count -> scan -> scatter; raises EOF / identity flags into d_flags[0]
 int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,

@@ -190,6 +190,7 @@ int bmpc_r1cs_eval(bmpc_ctx* ctx, const bmpc_csr* A, const bmpc_csr* B, const bm
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     const size_t nc = A->num_rows, nv = num_inputs + num_aux, total = nc + num_inputs;
     const size_t wi = (num_inputs + 63) / 64, wa = (num_aux + 63) / 64;
     UploadedCsr m[3];
@@ -247,6 +248,7 @@ int bmpc_generate_parameters(bmpc_ctx* ctx, const bmpc_csr* At, const bmpc_csr* 
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
+    StreamScope ss(ctx, st);
     memset(out, 0, sizeof(*out));
     // domain over the user constraints plus one `x * 0 = 0` row per input (generator.rs:273-275,294-297)
     const size_t nc = num_constraints + num_inputs;

@@ -7,7 +7,7 @@ gloo world_size-2 tests on CPU).
 
 Reference semantics preserved across ranks (multiexp.rs:55-65,244-249): EOF anywhere -> every
 window of the reference fails, so the global status follows the same precedence rule as the
-single-GPU path; see `combine_status`.
+single-GPU path; see `combine_flags`.
 """
 from __future__ import annotations
 
@@ -46,24 +46,30 @@ def slice_density(density_words, lo, hi):
     return np.packbits(bits, bitorder="little").view(np.uint64).copy()
 
 
-# raw flag bits produced by the MSM kernels (internal.h: MSM_FLAG_*) expressed as statuses:
-# a rank reports OK, UNEXPECTED_IDENTITY (consumed identity, top window of the reference or not is
-# resolved locally) or UNEXPECTED_EOF.  Across ranks: an EOF on any rank fails every reference
-# window; an identity that already won locally (its top-window digit was non-zero, or no EOF on that
-# rank) on a LOWER rank precedes it in scan order.
-def combine_status(statuses):
-    """statuses: list indexed by rank -> global status with the reference's precedence"""
-    first_eof = next((r for r, s in enumerate(statuses) if s == _lib.ERR_UNEXPECTED_EOF), None)
-    first_ident = next((r for r, s in enumerate(statuses) if s == _lib.ERR_UNEXPECTED_IDENTITY), None)
-    other = next((s for s in statuses if s not in (_lib.OK, _lib.ERR_UNEXPECTED_EOF, _lib.ERR_UNEXPECTED_IDENTITY)), None)
-    if other is not None:
-        return other
-    if first_eof is None:
-        return _lib.ERR_UNEXPECTED_IDENTITY if first_ident is not None else _lib.OK
-    # bases are consumed in position order, so only the last ranks can overrun; an identity status on
-    # a rank without EOF means "some consumed base is the identity", which beats the EOF only if the
-    # reference's top window consumes it -- ranks report that case as IDENTITY_TOP (see sharded_multiexp)
-    return _lib.ERR_UNEXPECTED_EOF
+# Raw flag bits produced by the MSM kernels (include/bellman_b200.h: BMPC_MSM_FLAG_*).  A shard
+# cannot decide the multiexp's status alone: the reference reports the first error in scan order
+# of its HIGHEST failing window (multiexp.rs:244-249).  An overrun (EOF) fails every window; an
+# identity base only the windows whose digit consumes it, and every position that still finds a
+# base precedes the overrun.  So the ranks exchange the raw words, OR them, and the rule is the
+# single-GPU one (csrc/api.cu: flags_to_status): EOF and IDENT_TOP -> UnexpectedIdentity, EOF alone
+# -> UnexpectedEof, no EOF and IDENT_ANY -> UnexpectedIdentity.  IDENT_TOP is computed against the
+# reference's window for the WHOLE exponent vector (n_total is passed into every shard call).
+FLAG_EOF, FLAG_IDENT_ANY, FLAG_IDENT_TOP = 1, 2, 4
+
+
+def flags_status(flags):
+    """status of a whole multiexp from the OR of all shards' flag words (== bmpc_msm_flags_status)"""
+    if flags & FLAG_EOF:
+        return _lib.ERR_UNEXPECTED_IDENTITY if flags & FLAG_IDENT_TOP else _lib.ERR_UNEXPECTED_EOF
+    return _lib.ERR_UNEXPECTED_IDENTITY if flags & FLAG_IDENT_ANY else _lib.OK
+
+
+def combine_flags(flag_words):
+    """flag_words: one raw word per rank -> global status with the reference's precedence"""
+    acc = 0
+    for f in flag_words:
+        acc |= int(f)
+    return flags_status(acc)
 
 
 def all_gather_bytes(local: bytes, group=None):
@@ -83,20 +89,24 @@ def all_gather_bytes(local: bytes, group=None):
 def sharded_multiexp(partial_fn, fold_fn, n, density_words, base_offset, group=None):
     """Host orchestration shared by the GPU path and the CPU tests.
 
-    partial_fn(lo, hi, first_base, density_slice) -> (status, partial_bytes)   this rank's slice
+    partial_fn(lo, hi, first_base, density_slice, n_total) -> (rc, flags, partial_bytes)
+        this rank's slice: rc = call status (OK unless the call itself failed), flags = raw
+        BMPC_MSM_FLAG_* word of the slice (bmpc_multiexp_shard_dev)
     fold_fn(list_of_partial_bytes) -> result                                   fold on every rank
     Returns (status, result or None)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_range(n, world, rank)
     first_base = base_offset + dense_before(density_words, lo)
-    status, partial = partial_fn(lo, hi, first_base, slice_density(density_words, lo, hi))
-    gathered = all_gather_bytes(bytes([status]) + bytes(partial), group)
-    statuses = [g[0] for g in gathered]
-    st = combine_status(statuses)
+    rc, flags, partial = partial_fn(lo, hi, first_base, slice_density(density_words, lo, hi), n)
+    gathered = all_gather_bytes(bytes([rc, flags]) + bytes(partial), group)
+    failed = next((g[0] for g in gathered if g[0] != _lib.OK), None)
+    if failed is not None:
+        return failed, None
+    st = combine_flags(g[1] for g in gathered)
     if st != _lib.OK:
         return st, None
-    return st, fold_fn([g[1:] for g in gathered])
+    return st, fold_fn([g[2:] for g in gathered])
 
 
 def gpu_sharded_multiexp(worker, bases_slice, scalars_dev_ptr, n_total, group=None, stream=None):
@@ -113,13 +123,19 @@ def gpu_sharded_multiexp(worker, bases_slice, scalars_dev_ptr, n_total, group=No
     lo, hi = shard_range(n_total, world, rank)
     dev = torch.device("cuda", worker.device)
     partial = torch.zeros(pbytes + 8, dtype=torch.uint8, device=dev)
-    st = lib.bmpc_multiexp_partial_dev(worker.ctx, bases_slice.handle, 0, scalars_dev_ptr, hi - lo, None, 0,
-                                       partial.data_ptr(), stream)
-    partial[pbytes] = st
+    flags = C.c_uint32(0)
+    rc = lib.bmpc_multiexp_shard_dev(worker.ctx, bases_slice.handle, 0, scalars_dev_ptr, hi - lo, None, 0, n_total,
+                                     partial.data_ptr(), C.byref(flags), stream)
+    partial[pbytes] = rc
+    partial[pbytes + 1] = flags.value
     gathered = torch.zeros(world * (pbytes + 8), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(gathered, partial, group=group)
     g = gathered.view(world, pbytes + 8)
-    status = combine_status([int(x) for x in g[:, pbytes].cpu().tolist()])
+    tail = g[:, pbytes:pbytes + 2].cpu().tolist()
+    failed = next((int(t[0]) for t in tail if int(t[0]) != _lib.OK), None)
+    if failed is not None:
+        return failed, None
+    status = combine_flags(int(t[1]) for t in tail)
     if status != _lib.OK:
         return status, None
     parts = g[:, :pbytes].contiguous()
@@ -174,12 +190,16 @@ class ProofShardPlan:
         for j, v in enumerate(self.base_offset):
             sh.base_offset[j] = v
         sh.h_lo, sh.h_hi = self.h_lo, self.h_hi
+        # lengths of the WHOLE exponent vectors (JOBS order): the reference's window follows them
+        ni, na = self.num_inputs, self.num_aux
+        for j, v in enumerate((ni, na, ni, na, ni, na, self.m - 1, na)):
+            sh.n_total[j] = v
         return sh
 
 
 def proof_partials(worker, params_slice, assignment, plan):
-    """One rank's share: (1920 partial-sum bytes, [8 statuses]).  `assignment` is the FULL
-    ProvingAssignment (host); the slices are taken here."""
+    """One rank's share: (1920 partial-sum bytes, [8 raw flag words]), or (None, call status) if the
+    call itself failed.  `assignment` is the FULL ProvingAssignment (host); the slices are taken here."""
     import ctypes as C
     asg = assignment
     w = worker
@@ -200,27 +220,27 @@ def proof_partials(worker, params_slice, assignment, plan):
     p = params_slice._struct()
     sh = plan.shard_struct()
     out = np.zeros(_lib.PROOF_PARTIAL_BYTES, dtype=np.uint8)
-    st = (C.c_int * 8)()
+    fl = (C.c_uint32 * 8)()
     rc = w._lib.bmpc_create_proof_partials(w.ctx, C.byref(p), C.byref(s), C.byref(sh),
-                                           C.c_void_p(out.ctypes.data), C.byref(st))
+                                           C.c_void_p(out.ctypes.data), C.byref(fl))
     if rc != _lib.OK:
-        return None, [rc] * 8
-    return out.tobytes(), [int(x) for x in st]
+        return None, rc
+    return out.tobytes(), [int(x) for x in fl]
 
 
-def proof_finish(worker, params, gathered_partials, statuses_by_rank, r_mont, s_mont):
+def proof_finish(worker, params, gathered_partials, flags_by_rank, r_mont, s_mont):
     """Fold the ranks' partial sums and run the tail (prover.rs:309-349).  Returns (status, proof):
     the subversion check on delta comes first, then the multiexp statuses in the order the
-    reference awaits them (prover.rs:328-343), each combined over the ranks."""
+    reference awaits them (prover.rs:328-343), each from the OR of the ranks' flag words."""
     import ctypes as C
     w = worker
     if (params.delta_g1[0] & 0x40) or (params.delta_g2[0] & 0x40):
         return _lib.ERR_UNEXPECTED_IDENTITY, None
     for j in range(8):
-        st = combine_status([ranks[j] for ranks in statuses_by_rank])
+        st = combine_flags(ranks[j] for ranks in flags_by_rank)
         if st != _lib.OK:
             return st, None
-    world = len(statuses_by_rank)
+    world = len(flags_by_rank)
     blob = np.frombuffer(b"".join(gathered_partials), dtype=np.uint8)
     assert blob.size == world * _lib.PROOF_PARTIAL_BYTES
     p = params._struct()
@@ -236,10 +256,15 @@ def proof_finish(worker, params, gathered_partials, statuses_by_rank, r_mont, s_
 def create_proof_sharded(assignment, params_slice, r_mont, s_mont, plan, group=None):
     """create_proof (prover.rs:206-350) on all ranks of `group`: every rank calls this with its
     slice of the parameters; every rank gets the 192-byte proof.  One all-gather of 1928 bytes."""
-    partial, statuses = proof_partials(params_slice.worker, params_slice, assignment, plan)
-    local = (partial if partial is not None else bytes(_lib.PROOF_PARTIAL_BYTES)) + bytes(statuses)
-    gathered = all_gather_bytes(local, group)
+    partial, flags = proof_partials(params_slice.worker, params_slice, assignment, plan)
+    rc = _lib.OK
+    if partial is None:
+        rc, partial, flags = flags, bytes(_lib.PROOF_PARTIAL_BYTES), [0] * 8
+    gathered = all_gather_bytes(partial + bytes(flags) + bytes([rc]), group)
     nb = _lib.PROOF_PARTIAL_BYTES
+    failed = next((g[nb + 8] for g in gathered if g[nb + 8] != _lib.OK), None)
+    if failed is not None:
+        return failed, None
     return proof_finish(params_slice.worker, params_slice, [g[:nb] for g in gathered],
                         [list(g[nb:nb + 8]) for g in gathered], r_mont, s_mont)
 

@@ -122,48 +122,81 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------ reference arm
+def dlog_progression(seed):
+    """(first, step) of the reference arm's bases P_i = (first + i step) G: discrete logs spread over
+    the whole scalar field, still known in closed form for the result check"""
+    import random
+    from oracle import fields
+    rng = random.Random(seed)
+    return rng.randrange(1, fields.Fr.p), rng.randrange(1, fields.Fr.p)
+
+
+def limbs_to_int(l):
+    return sum(int(l[j]) << (64 * j) for j in range(4))
+
+
+def int_to_limbs(v):
+    return np.array([(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+
+
 def run_reference(args):
-    """CPU restatement of the reference's multiexp (oracle/c, pthreads, one task per window as
-    multiexp.rs:238-242) on all host cores; each step is a bounded sample of the workload."""
+    """The reference's CPU multiexp (multiexp.rs:159-281) as restated in oracle/c (64-bit-limb
+    Montgomery, one task per window as multiexp.rs:238-242, pthreads) on all host cores, at the
+    STATED configuration: uniform 254-bit scalars, bases with field-wide discrete logs, and the window
+    the reference picks for 2^log_n exponents (c = 17, 15 windows at 2^24).  Each step is one multiexp
+    over a 2^ref_sample_log-point sample of that vector (default 2^23: the per-window bucket sums the
+    sample pays once per step cost 3 % of its additions, so the per-point cost is the full vector's
+    to within that), result checked against (sum k_i s_i) G."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import ctypes as C
-
-    from oracle import cref
+    from oracle import cref, fields
     lib = cref.load()
-    lib.orc_bases_g1_sequence.restype = C.c_void_p
-    lib.orc_bases_g1_sequence.argtypes = [C.c_size_t, C.c_uint64]
     threads = cref.hardware_threads()
-    sample_log = args.ref_sample_log
+    n_full = 1 << args.log_n
+    sample_log = min(args.ref_sample_log, args.log_n)
     n = 1 << sample_log
-    bases = cref.CBases(1, lib.orc_bases_g1_sequence(n, 1))
+    first, step = dlog_progression(2)
+    t_setup = time.perf_counter()
+    bases = cref.bases_g1_progression(n, first, step)
+    t_setup = time.perf_counter() - t_setup
     scalars = rand_limbs(n, 1)
+    c_ref = int(lib.orc_window_size(n_full))
     for _ in range(args.warmup):
-        cref.multiexp(bases, 0, scalars, threads=threads)
+        cref.multiexp_window(bases, 0, scalars, n_full, threads=threads)
     t0 = time.perf_counter()
     out = None
     for _ in range(args.steps):
-        st, out = cref.multiexp(bases, 0, scalars, threads=threads)
+        st, out = cref.multiexp_window(bases, 0, scalars, n_full, threads=threads)
         assert st == 0
     dt = (time.perf_counter() - t0) / args.steps
-    ks = np.zeros((n, 4), dtype=np.uint64)
-    ks[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
-    ok = out == cref.g1_generator_mul(cref.fr_dot(ks, scalars))
+    ones = np.zeros((n, 4), dtype=np.uint64)
+    ones[:, 0] = 1
+    idx = np.zeros((n, 4), dtype=np.uint64)
+    idx[:, 0] = np.arange(n, dtype=np.uint64)
+    q = fields.Fr.p
+    k = (first * limbs_to_int(cref.fr_dot(ones, scalars)) + step * limbs_to_int(cref.fr_dot(idx, scalars))) % q
+    ok = out == cref.g1_generator_mul(int_to_limbs(k))
     value = n / dt / 1e6
-    sample = f"G1 multiexp over a 2^{sample_log}-point sample of the 2^{args.log_n} workload, window c={lib.orc_window_size(n)}"
+    windows = (255 + c_ref - 1) // c_ref
+    sample = (f"G1 multiexp over a 2^{sample_log}-point sample of the 2^{args.log_n} vector per step, reference window "
+              f"c={c_ref} ({windows} windows = {windows} tasks, multiexp.rs:238-242,267-271) as for the whole vector")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u64-limb Montgomery (CPU)", "data": "synthetic",
-        "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity",
-                   "bases": "k_i*G (known discrete logs)", "sample": sample},
+        "config": {"workload": f"G1 multiexp 2^{args.log_n} points, uniform 254-bit scalars, FullDensity "
+                               f"(BASELINE configs[1] shape at the size the metric is quoted on)",
+                   "bases": "(a + i b) G with random 255-bit a, b (field-wide known discrete logs)", "sample": sample,
+                   "window_bits": c_ref, "windows": windows, "setup_s": round(t_setup, 2)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "result_checked": bool(ok)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "result_checked": bool(ok),
     }
     print(json.dumps(line), flush=True)
+    if not ok:
+        sys.exit(3)
 
 
 # -------------------------------------------------------------------------------- our arm
@@ -294,43 +327,66 @@ def run_ours(args):
         e2e_ms = float(t.item())
     assert out.tobytes() == result_resident
 
+    # ---- the headline result itself: (sum over all ranks of sum_i k_i s_i) G, no MSM involved
+    result_checked = None
+    if rank == 0:
+        from oracle import cref as _cref, fields as _fields
+        tot = 0
+        for r in range(world):
+            ks_r = ks if r == 0 else rand_limbs(n, 2 + 7919 * r)
+            sc_r = scalars_h.numpy().view(np.uint64) if r == 0 else rand_limbs(n, 1 + 7919 * r)
+            tot += limbs_to_int(_cref.fr_dot(ks_r, sc_r))
+        tot %= _fields.Fr.p
+        if grp == bm.G1:
+            expect = _cref.g1_generator_mul(int_to_limbs(tot))
+        else:
+            from oracle import curves as _curves
+            expect = _curves.G2.to_uncompressed(_curves.G2.mul(_curves.G2.gen, tot))
+        result_checked = bool(expect == result_resident)
+
     peaks = measured_peaks()
     acc_ms, acc_cnt = prof["accumulate"]
-    roofline = {
-        "kernel": "msm_accumulate_kernel<%s>" % ("Fp" if grp == bm.G1 else "Fp2"), "bound": "hbm",
-        "achieved": bytes_per_point * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": (bytes_per_point * n / (acc_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if acc_ms else None,
-        "traffic": peaks.get("acc_traffic_bytes") if (world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute) else None,
-        "traffic_source": "profiles/r01_ncu_kernel_summaries.json (ncu --set full, same command, 1 GPU, 2^24; affine kernel: r01d capture)",
-        "algorithmic_bytes": bytes_per_point * n,
-        "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
-        "kernel_ms": acc_ms, "share_of_step": acc_ms / ms if ms else None,
-        "note": "integer-pipe bound, not HBM bound: see roofline_int",
-    }
-    roofline_int = None
     cw, ww, hh = C.c_uint32(), C.c_uint32(), C.c_uint32()
     lib.bmpc_msm_geometry(w.ctx, bases.handle, n, C.byref(cw), C.byref(ww), C.byref(hh))
     ainfo = (C.c_uint32 * 8)()
     lib.bmpc_msm_accumulate_info(w.ctx, bases.handle, n, C.byref(ainfo))
-    affine = bool(ainfo[0])
-    if affine:
-        # batched-affine tree: 6 products per addition (1 running product, 2 to unwind it, slope,
-        # slope^2, y3); the shared inversion and its product tree are overhead, not counted
-        mul_per_add = 6 * (1 if grp == bm.G1 else 3)
-        roofline["kernel"] = "msm_accumulate_affine_kernel<%s>" % ("Fp" if grp == bm.G1 else "Fp2")
-        roofline["traffic"] = peaks.get("aff_traffic_bytes") if (world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute) else None
+    acc_mode = int(ainfo[0])
+    kname = {0: "msm_accumulate_kernel", 1: "msm_accumulate_affine_kernel", 2: "msm_pair_round_kernel"}[acc_mode]
+    kname += "<%s>" % ("Fp" if grp == bm.G1 else "Fp2")
+    headline_cfg = world == 1 and args.log_n == 24 and grp == bm.G1 and not args.no_precompute
+    traffic = None
+    if headline_cfg:
+        traffic = {0: peaks.get("acc_traffic_bytes"), 1: peaks.get("aff_traffic_bytes"),
+                   2: peaks.get("pair_traffic_bytes")}[acc_mode]
+    # The bucket accumulation is bound by the 32-bit multiplier pipe, so THAT is the roofline:
+    # field products of the point additions actually issued (W windows per point; 10 per XYZZ mixed
+    # addition, 6 per batched-affine addition: 1 running product, 2 to unwind it, slope, slope^2, y3;
+    # the shared inversion and its product tree are overhead, not counted) x 300 MAC32 per Fp product,
+    # against the measured mad.lo.cc/madc.hi.cc rate of this GPU.
+    mul_per_add = (10 if acc_mode == 0 else 6) * (1 if grp == bm.G1 else 3)
+    roofline = None
     if peaks.get("mac32_per_s") and acc_ms:
-        executed = mul_per_add * 300 * ww.value * n   # field products of the additions actually issued
+        executed = mul_per_add * 300 * ww.value * n
         ach = executed / (acc_ms * 1e-3)
-        roofline_int = {"kernel": roofline["kernel"], "bound": "int32-mac",
-                        "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12, "unit": "TMAC32/s",
-                        "frac": ach / peaks["mac32_per_s"],
-                        "peak_source": "profiles/r01_imad_peak.json (mad.lo.cc/madc.hi.cc chains, measured)",
-                        "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp mul x 300 MAC32 per point"
-                                + (f" (batched-affine tree, {ainfo[1]} slices per job, {ainfo[2]} additions per inversion per thread)" if affine else " (XYZZ mixed addition 8M+2S)"),
-                        "survey_model_frac": (G1_MSM_MAC32_PER_POINT if grp == bm.G1 else G2_MSM_MAC32_PER_POINT) * n / (acc_ms * 1e-3) / peaks["mac32_per_s"],
-                        "survey_model": "48000 MAC32 per point (SURVEY 8d: fixed 16 windows)"}
+        roofline = {"kernel": kname, "bound": "int32-mac", "achieved": ach / 1e12, "peak": peaks["mac32_per_s"] / 1e12,
+                    "unit": "TMAC32/s", "frac": ach / peaks["mac32_per_s"],
+                    "traffic": traffic, "algorithmic_bytes": bytes_per_point * n,
+                    "traffic_ratio": (traffic / (bytes_per_point * n)) if traffic else None,
+                    "traffic_source": "profiles/ (ncu --set full of this command, 1 GPU, 2^24): dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                    "peak_source": "profiles/r01_imad_peak.json (bench/imad_peak.cu on this pool's B200: 32 MAC32/clk/SM)",
+                    "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp products x 300 MAC32 per point",
+                    "kernel_ms": acc_ms, "launches_per_step": acc_cnt // max(args.steps, 1),
+                    "share_of_step": acc_ms * (acc_cnt // max(args.steps, 1)) / ms if ms else None,
+                    "ncu_fmaheavy_pct": peaks.get("fmaheavy_pct") if headline_cfg else None,
+                    "survey_model_frac": None,
+                    "survey_model_note": "SURVEY 8d charges 48000 MAC32 per point (16 windows x 10 products); this path "
+                                         "issues fewer products than that model, so a fraction against it would exceed 1 and is not reported"}
+    hbm_ach = bytes_per_point * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None
+    roofline_hbm = {"kernel": kname, "bound": "hbm", "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (hbm_ach / peaks["hbm_gbs"]) if hbm_ach else None,
+                    "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})",
+                    "dram_gbs_measured": (traffic / (acc_ms * 1e-3) / 1e9) if (traffic and acc_ms) else None,
+                    "note": "not the binding roofline: algorithmic bytes (128 B per point) over the kernel time"}
 
     line = {
         "metric": METRIC if (grp == bm.G1 and args.log_n == 24) else f"{args.group}_msm_mpts_per_s_2p{args.log_n}",
@@ -341,33 +397,59 @@ def run_ours(args):
                                f"(BASELINE configs[1] shape at the size the metric is quoted on)",
                    "bases": "k_i*G, resident (CRS registered once%s)" % ("" if args.no_precompute else
                             ", window tables 2^(cw)*P_i precomputed at registration"), "points_per_gpu": n,
-                   "l2": "inputs larger than L2 (scalars %d MiB + bases %d MiB per GPU)" % (n * 32 >> 20, n * 96 >> 20),
+                   "l2": "inputs larger than L2 (scalars %d MiB + bases %d MiB per GPU%s)" % (
+                       n * 32 >> 20, n * pt_bytes >> 20,
+                       "" if args.no_precompute else "; with the %d window tables %d MiB per GPU" % (ww.value, ww.value * n * pt_bytes >> 20)),
+                   "table_bytes_per_gpu": 0 if args.no_precompute else ww.value * n * pt_bytes,
                    "parallelism": f"bases split x{world}, all-gather of {pbytes}-byte partials" if world > 1 else "single GPU",
                    "setup_s": round(t_setup, 2)},
         "clocks": clocks.summary(),
         "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96 + 64},
-        "gpu_launches": launches,
-        "roofline": roofline, "roofline_int": roofline_int,
+        "gpu_launches": launches, "result_checked": result_checked,
+        "roofline": roofline, "roofline_hbm": roofline_hbm,
         "kernel_ms": {k: v[0] for k, v in prof.items()},
     }
 
-    # ---- CPU baseline beside it (rank 0, N = 1): oracle on a bounded sample + parity check
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle's C port on a bounded sample of the same
+    # vector, with the window the reference picks for the WHOLE vector (c = 17 at 2^24), + parity check
     if world == 1 and not args.no_cpu_baseline and grp == bm.G1:
         from oracle import cref
         threads = cref.hardware_threads()
-        slog = args.ref_sample_log
+        slog = min(args.cpu_sample_log, args.log_n)
         ns = 1 << slog
         cb = cref.CBases.from_uncompressed(1, bases.read(0, ns))
         sc = np.ascontiguousarray(scalars_h.numpy().view(np.uint64)[:ns])
         t0 = time.perf_counter()
-        st, cpu_out = cref.multiexp(cb, 0, sc, threads=threads)
+        st, cpu_out = cref.multiexp_window(cb, 0, sc, n, threads=threads)
         cpu_s = time.perf_counter() - t0
         gpu_out = bm.multiexp(w, (bases, 0), bm.FullDensity(), sc).wait()
+        c_ref = int(cref.load().orc_window_size(n))
         line["cpu_baseline"] = {"value": ns / cpu_s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"first 2^{slog} points of the workload, reference window c={cref.load().orc_window_size(ns)}",
+                                "sample": f"first 2^{slog} points of the workload, reference window c={c_ref} "
+                                          f"({(255 + c_ref - 1) // c_ref} windows) as for the whole 2^{args.log_n} vector",
                                 "seconds": cpu_s, "matches_gpu_bytes": bool(st == 0 and cpu_out == gpu_out)}
         cb.free()
+
+    # ---- the same multiexp over bases WITHOUT window tables (a base vector that is not a resident CRS)
+    if world == 1 and not args.no_precompute and not args.no_plain and grp == bm.G1:
+        try:
+            plain = bm.Bases.fixed_base_mul(w, grp, curves_gen, ks)
+            for _ in range(2):
+                st = lib.bmpc_multiexp_dev(w.ctx, plain.handle, 0, scalars_d.data_ptr(), n, None, 0, optr, stream)
+                assert st == 0
+            same = out.tobytes() == result_resident
+            bases_keep, bases = bases, plain
+            ms_plain = timed(lambda: step_resident(scalars_d.data_ptr()), max(2, args.steps // 2))
+            bases = bases_keep
+            cp, wp, hp = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            lib.bmpc_msm_geometry(w.ctx, plain.handle, n, C.byref(cp), C.byref(wp), C.byref(hp))
+            line["no_precompute"] = {"value": n_total / (ms_plain * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_plain,
+                                     "window_bits": cp.value, "windows": wp.value, "bucket_sets": hp.value,
+                                     "same_result_bytes": bool(same)}
+            plain.free()
+        except Exception as e:
+            line["no_precompute"] = {"error": repr(e)}
 
     # ---- Groth16 prove @ 2^prove_log_n (N = 1), same run
     if world == 1 and not args.no_prove and grp == bm.G1:
@@ -483,7 +565,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--group", default="g1", choices=["g1", "g2"])
-    ap.add_argument("--ref-sample-log", type=int, default=18)
+    ap.add_argument("--ref-sample-log", type=int, default=23,
+                    help="reference arm: points per step (a sample of the 2^log_n vector, window as for the whole vector)")
+    ap.add_argument("--cpu-sample-log", type=int, default=22, help="cpu_baseline leg of our arm: sample size")
+    ap.add_argument("--no-plain", action="store_true", help="skip the table-free timing of the same multiexp")
     ap.add_argument("--prove-log-n", type=int, default=22)
     ap.add_argument("--no-prove", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

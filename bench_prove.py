@@ -213,7 +213,9 @@ def prove_bench_sharded(w, log_m, steps, world, rank, precompute=True):
     return res
 
 
-def prove_bench(w, log_m, steps, no_cpu_baseline=False, cpu_sample_log=16, precompute=True):
+def prove_bench(w, log_m, steps, no_cpu_baseline=False, cpu_sample_log=None, precompute=True):
+    """cpu_sample_log None: the CPU restatement proves the SAME 2^log_m workload once (the stated
+    configuration; ~40 s on 16 cores at 2^22)."""
     import torch
     wl = Workload(w, log_m, precompute=precompute)
     wl.prove()                                     # warm-up (tables, arena)
@@ -242,17 +244,26 @@ def prove_bench(w, log_m, steps, no_cpu_baseline=False, cpu_sample_log=16, preco
         res["matches_known_dlog_expectation"] = bool(proof == wl.expected_proof())
         res["check_s"] = round(time.perf_counter() - t0, 2)
         threads = cref.hardware_threads()
-        small = Workload(w, cpu_sample_log, precompute=precompute)
-        gp = small.prove()
-        st, cp, dt = small.cpu_reference_proof(threads)
-        res["cpu_baseline"] = {"value": dt, "unit": "s", "cores": threads, "kind": "port",
-                               "sample": f"same generator at 2^{cpu_sample_log} constraints (full prove)",
-                               "matches_gpu_bytes": bool(st == 0 and cp == gp),
-                               "gpu_seconds_same_sample": None}
-        t0 = time.perf_counter()
-        small.prove()
-        res["cpu_baseline"]["gpu_seconds_same_sample"] = time.perf_counter() - t0
-        small.free()
+        if cpu_sample_log is None or cpu_sample_log >= log_m:
+            st, cp, dt = wl.cpu_reference_proof(threads)
+            res["cpu_baseline"] = {"value": dt, "unit": "s", "cores": threads, "kind": "port",
+                                   "sample": f"the same 2^{log_m}-constraint workload, proved once (prover.rs:206-350 "
+                                             "restated in oracle/c: 7 transforms + 8 multiexps, one task per window)",
+                                   "matches_gpu_bytes": bool(st == 0 and cp == proof),
+                                   "gpu_seconds_same_sample": min(times),
+                                   "speedup": dt / min(times)}
+        else:
+            small = Workload(w, cpu_sample_log, precompute=precompute)
+            gp = small.prove()
+            st, cp, dt = small.cpu_reference_proof(threads)
+            res["cpu_baseline"] = {"value": dt, "unit": "s", "cores": threads, "kind": "port",
+                                   "sample": f"same generator at 2^{cpu_sample_log} constraints (full prove)",
+                                   "matches_gpu_bytes": bool(st == 0 and cp == gp),
+                                   "gpu_seconds_same_sample": None}
+            t0 = time.perf_counter()
+            small.prove()
+            res["cpu_baseline"]["gpu_seconds_same_sample"] = time.perf_counter() - t0
+            small.free()
     # Parameters::read ingestion on a 2^18-constraint CRS: write, then read back
     try:
         pw = Workload(w, 18)

@@ -24,8 +24,13 @@
  *   - every function returns a bmpc_status; there is NO CPU fallback: without a usable
  *     CUDA device calls fail with BMPC_ERR_CUDA
  *   - "_dev" variants take device pointers (inputs already resident in HBM) and a
- *     cudaStream_t passed as void*; the plain variants take host pointers and include the
- *     host<->device copies
+ *     cudaStream_t passed as void* (NULL = the context's own stream); the plain variants take host
+ *     pointers and include the host<->device copies
+ *   - stream contract: a context's scratch arena, twiddle tables and staging words are shared by
+ *     all its calls.  Calls are serialised by a mutex on the host; on the device a call issued on
+ *     another stream than the context's previous call first waits for that call (event), so
+ *     asynchronous "_dev" calls on different streams never overlap on the shared state.  Use one
+ *     context per concurrent stream to overlap work.
  */
 #ifndef BELLMAN_B200_H
 #define BELLMAN_B200_H
@@ -123,6 +128,21 @@ int  bmpc_multiexp_partial_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t ba
                                const uint64_t* d_scalars, size_t n,
                                const uint64_t* d_density_words, size_t density_len,
                                void* d_partial_out, void* stream);
+/* One shard of a multiexp whose exponent vector has n_total (>= n) entries in all: same as
+ * bmpc_multiexp_partial_dev, but the error conditions come back as the raw flag word instead of a
+ * status, because which error the reference reports depends on ALL shards (multiexp.rs:244-249:
+ * the first error in scan order of the highest failing window; the window size follows n_total,
+ * :267-271).  The caller ORs the flag words of all shards and asks bmpc_msm_flags_status.
+ * Returns BMPC_OK unless the call itself failed (arguments, CUDA). */
+enum { BMPC_MSM_FLAG_EOF = 1,        /* a dense position maps past the end of the bases          */
+       BMPC_MSM_FLAG_IDENT_ANY = 2,  /* a consumed base (dense, scalar != 0) is the identity     */
+       BMPC_MSM_FLAG_IDENT_TOP = 4   /* ... and its digit in the reference's top window is != 0  */ };
+int  bmpc_multiexp_shard_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                             const uint64_t* d_scalars, size_t n,
+                             const uint64_t* d_density_words, size_t density_len, size_t n_total,
+                             void* d_partial_out, uint32_t* flags_out, void* stream);
+/* status of a whole multiexp from the OR of its shards' flag words (SURVEY 8a'/5) */
+int  bmpc_msm_flags_status(uint32_t flags_or);
 int  bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count,
                        uint8_t* out, void* stream);
 size_t bmpc_partial_bytes(int group);
@@ -244,15 +264,17 @@ int  bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assi
  *     sums (6 x 192 B G1, then 2 x 384 B G2) and the eight multiexp statuses.
  *   bmpc_create_proof_finish: `partials_all` = world x BMPC_PROOF_PARTIAL_BYTES gathered from all
  *     ranks (any collective: 1920 B per rank); folds them, runs prover.rs:309-349, writes the proof.
- *     The caller combines the statuses first (bellman_mpc_b200/dist.py::combine_status). */
+ *     The caller first ORs the flag words per multiexp over the ranks and resolves them with
+ *     bmpc_msm_flags_status in the order above (bellman_mpc_b200/dist.py::combine_flags). */
 #define BMPC_PROOF_PARTIAL_BYTES 1920
 typedef struct {
     size_t base_offset[8];
     size_t h_lo, h_hi;
+    size_t n_total[8];
 } bmpc_proof_shard;
 int  bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* params, const bmpc_assignment* asg,
                                 const bmpc_proof_shard* shard, uint8_t partials_out[BMPC_PROOF_PARTIAL_BYTES],
-                                int statuses_out[8]);
+                                uint32_t flags_out[8]);
 int  bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* params, const uint8_t* partials_all, size_t world,
                               const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
 
@@ -310,8 +332,9 @@ int  bmpc_batch_scalar_mul(bmpc_ctx* ctx, const bmpc_bases* in, const uint64_t* 
  * loop over a G1 and a G2 list): out has list.len() elements, out[i] = sum_j coeffs[j] * list[cols[j]]
  * over CSR row i (entries row_ptr[i] .. row_ptr[i+1]) for the rows BEFORE the first empty one (the
  * reference `break`s there, :432-434); every later element is the identity.  coeffs canonical 4 x u64
- * per entry.  BMPC_ERR_LENGTH_MISMATCH where the reference panics on an index: n_rows > list.len()
- * or a live column >= list.len(). */
+ * per entry.  BMPC_ERR_LENGTH_MISMATCH where the reference panics on an index: more live rows than
+ * list.len() (a taller matrix whose first empty row comes before row list.len() is fine, as in the
+ * reference) or a live column >= list.len(). */
 int  bmpc_list_mul_matrix(bmpc_ctx* ctx, const bmpc_bases* list, const uint64_t* row_ptr,
                           const uint32_t* cols, const uint64_t* coeffs, size_t n_rows, bmpc_bases** out);
 /* out[i] = base * k[i]; base uncompressed big-endian; scalars canonical (host or device) */

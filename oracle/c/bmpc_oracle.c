@@ -134,9 +134,17 @@ static void mexp_task(void* arg, size_t idx) {
 }
 
 /* multiexp_inner + the fold (multiexp.rs:238-249).  out: g1_t or g2_t.  Returns status. */
+static int multiexp_any_c(int group, const void* bases, size_t nbases, size_t start, const uint64_t* exps,
+                          size_t n, const uint64_t* density, int threads, uint32_t c, void* out);
 static int multiexp_any(int group, const void* bases, size_t nbases, size_t start, const uint64_t* exps,
                         size_t n, const uint64_t* density, int threads, void* out) {
-    uint32_t c = orc_window_size(n);
+    return multiexp_any_c(group, bases, nbases, start, exps, n, density, threads, orc_window_size(n), out);
+}
+/* c given by the caller: bench.py times a SAMPLE of a larger exponent vector with the window the
+ * reference picks for the whole vector (multiexp.rs:267-271), so the per-point work is the stated
+ * configuration's. */
+static int multiexp_any_c(int group, const void* bases, size_t nbases, size_t start, const uint64_t* exps,
+                          size_t n, const uint64_t* density, int threads, uint32_t c, void* out) {
     size_t nwin = (255 + c - 1) / c; /* (0..NUM_BITS).step_by(c) */
     size_t psz = group == 1 ? sizeof(g1_t) : sizeof(g2_t);
     void* parts = malloc(nwin * psz);
@@ -246,16 +254,28 @@ orc_bases_t* orc_bases_from_mont(int group, const uint64_t* data, size_t n) {
 }
 /* Synthetic G1 bases with known discrete logs for the CPU-only reference arm of bench.py:
  * P_i = (first + i) * G, built by repeated mixed addition and one batch inversion. */
+static orc_bases_t* bases_g1_progression(size_t n, const uint64_t first[4], const uint64_t step[4]);
 orc_bases_t* orc_bases_g1_sequence(size_t n, uint64_t first) {
+    uint64_t a[4] = {first, 0, 0, 0}, one[4] = {1, 0, 0, 0};
+    return bases_g1_progression(n, a, one);
+}
+/* P_i = (first + i * step) * G for 256-bit first, step: bases whose discrete logs are spread over
+ * the whole scalar field (the reference arm's "uniform random bases"), still known in closed form */
+orc_bases_t* orc_bases_g1_progression(size_t n, const uint64_t first[4], const uint64_t step[4]) {
+    return bases_g1_progression(n, first, step);
+}
+static orc_bases_t* bases_g1_progression(size_t n, const uint64_t first[4], const uint64_t step[4]) {
     orc_bases_t* b = (orc_bases_t*)malloc(sizeof(*b));
     b->group = 1; b->n = n;
     g1_affine_t* out = (g1_affine_t*)malloc((n ? n : 1) * sizeof(g1_affine_t));
     b->pts = out;
     if (!n) return b;
     g1_affine_t gen; memcpy(gen.x.l, G1_GEN_X, 48); memcpy(gen.y.l, G1_GEN_Y, 48); gen.inf = 0;
-    g1_t g, cur; g1_from_affine(&g, &gen);
-    uint64_t k[4] = {first, 0, 0, 0};
-    g1_mul(&cur, &g, k);
+    g1_t g, cur, stp; g1_from_affine(&g, &gen);
+    g1_mul(&cur, &g, first);
+    g1_mul(&stp, &g, step);
+    g1_affine_t stp_a; g1_to_affine(&stp_a, &stp);
+    gen = stp_a;                      /* the loop below adds `gen` per element */
     g1_t* proj = (g1_t*)malloc(n * sizeof(g1_t));
     fp_t* pre = (fp_t*)malloc(n * sizeof(fp_t));
     fp_t acc; fp_one(&acc);
@@ -293,6 +313,24 @@ int orc_multiexp(const orc_bases_t* b, size_t start, const uint64_t* exps, size_
     } else {
         g2_t r; g2_affine_t a;
         int st = multiexp_any(2, b->pts, b->n, start, exps, n, density, threads, &r);
+        if (st) return st;
+        g2_to_affine(&a, &r); orc_g2_to_uncompressed(&a, out);
+    }
+    return 0;
+}
+
+/* same with the window of an n_window-entry exponent vector (n_window >= n; G1, FullDensity use) */
+int orc_multiexp_window(const orc_bases_t* b, size_t start, const uint64_t* exps, size_t n,
+                        size_t n_window, int threads, uint8_t* out) {
+    uint32_t c = orc_window_size(n_window);
+    if (b->group == 1) {
+        g1_t r; g1_affine_t a;
+        int st = multiexp_any_c(1, b->pts, b->n, start, exps, n, NULL, threads, c, &r);
+        if (st) return st;
+        g1_to_affine(&a, &r); orc_g1_to_uncompressed(&a, out);
+    } else {
+        g2_t r; g2_affine_t a;
+        int st = multiexp_any_c(2, b->pts, b->n, start, exps, n, NULL, threads, c, &r);
         if (st) return st;
         g2_to_affine(&a, &r); orc_g2_to_uncompressed(&a, out);
     }

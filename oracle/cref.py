@@ -55,6 +55,12 @@ def load():
     lib.orc_bases_len.argtypes = [vp]
     lib.orc_multiexp.restype = i32
     lib.orc_multiexp.argtypes = [vp, sz, vp, sz, vp, sz, i32, vp]
+    lib.orc_multiexp_window.restype = i32
+    lib.orc_multiexp_window.argtypes = [vp, sz, vp, sz, sz, i32, vp]
+    lib.orc_bases_g1_progression.restype = vp
+    lib.orc_bases_g1_progression.argtypes = [sz, vp, vp]
+    lib.orc_bases_g1_sequence.restype = vp
+    lib.orc_bases_g1_sequence.argtypes = [sz, C.c_uint64]
     lib.orc_naive_multiexp.restype = i32
     lib.orc_naive_multiexp.argtypes = [vp, vp, sz, vp]
     lib.orc_g1_generator_mul.argtypes = [vp, vp]
@@ -105,6 +111,22 @@ def multiexp(bases, start, exps, density_words=None, threads=1):
     dw = None if density_words is None else np.ascontiguousarray(density_words, dtype=np.uint64)
     st = load().orc_multiexp(bases.handle, start, _p(exps), n, _p(dw), n if dw is not None else 0, threads, _p(out))
     return st, out.tobytes()
+
+
+def multiexp_window(bases, start, exps, n_window, threads=1):
+    """FullDensity multiexp over `exps` with the window the reference picks for an n_window-entry
+    exponent vector (multiexp.rs:267-271): a bounded SAMPLE of a larger workload at that workload's
+    per-point cost."""
+    exps = np.ascontiguousarray(exps, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros(96 if bases.group == 1 else 192, dtype=np.uint8)
+    st = load().orc_multiexp_window(bases.handle, start, _p(exps), exps.shape[0], n_window, threads, _p(out))
+    return st, out.tobytes()
+
+
+def bases_g1_progression(n, first, step):
+    """CBases of P_i = (first + i * step) * G (first, step: Python ints < q)"""
+    lim = lambda v: np.array([(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+    return CBases(1, load().orc_bases_g1_progression(n, _p(lim(first)), _p(lim(step))))
 
 
 def naive_multiexp(bases, exps):

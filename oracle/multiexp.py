@@ -167,3 +167,45 @@ def naive(group, bases, exponents):
     for b, e in zip(bases, exponents):
         acc = group.add(acc, group.mul(b, e))
     return acc
+
+
+# ---- sharded form: what one shard of a multiexp can know on its own ------------------
+FLAG_EOF, FLAG_IDENT_ANY, FLAG_IDENT_TOP = 1, 2, 4      # include/bellman_b200.h: BMPC_MSM_FLAG_*
+
+
+def shard_flags(group, bases, first_base, density_bits, exponents, n_total, num_bits=None):
+    """Error conditions of the exponent slice `exponents` (its first dense position consumes
+    bases[first_base]) of a multiexp over n_total exponents, as flag bits.  Derived from
+    multiexp.rs:55-65,74-80,191-223: EOF = some dense position finds the cursor at or past the end;
+    IDENT_ANY = some window calls next() on an identity base (dense, exponent != 0); IDENT_TOP = the
+    reference's HIGHEST window (skip = largest multiple of c below num_bits, c from n_total,
+    :238-242,267-271) does.  `flags_status` of the OR over all shards is the status of the whole
+    multiexp, because every position below the end of the bases precedes the overrun in scan order."""
+    c = window_size(n_total)
+    if num_bits is None:
+        num_bits = group.scalar_field.NUM_BITS
+    top_skip = ((num_bits - 1) // c) * c
+    flags, idx = 0, first_base
+    for exp, dense in zip(exponents, density_bits):
+        if not dense:
+            continue
+        if idx >= len(bases):
+            flags |= FLAG_EOF
+        elif exp != 0 and group.is_identity(bases[idx]):
+            flags |= FLAG_IDENT_ANY
+            if exp == 1:
+                top = top_skip == 0                             # next() only in window 0 (:201-206)
+            else:
+                top = ((exp >> top_skip) & ((1 << c) - 1)) != 0
+            if top:
+                flags |= FLAG_IDENT_TOP
+        idx += 1
+    return flags
+
+
+def flags_status(flags):
+    """'eof' | 'identity' | None for the OR of all shards' flags (multiexp.rs:244-249: try_fold over
+    the windows from the highest down; EOF fails every window, an identity only those consuming it)."""
+    if flags & FLAG_EOF:
+        return "identity" if flags & FLAG_IDENT_TOP else "eof"
+    return "identity" if flags & FLAG_IDENT_ANY else None

@@ -18,13 +18,19 @@ from oracle import multiexp as ome
 P = fields.DummyFr.p
 
 
-def _case(seed, n=203, nbases=None):
+def _case(seed, n=203, nbases=None, ident=None):
+    """ident = (position, exponent): the base that dense position consumes becomes the identity"""
     rng = random.Random(seed)
     bits = [rng.random() < 0.6 for _ in range(n)]
     if nbases is None:
         nbases = 3 + sum(bits) + 2
     bases = [rng.randrange(1, P) for _ in range(nbases)]
     exps = [rng.choice([0, 1, rng.randrange(P)]) for _ in range(n)]
+    if ident is not None:
+        pos, e = ident
+        bits[pos] = True
+        exps[pos] = e
+        bases[3 + sum(bits[:pos])] = 0           # Dummy group: 0 is the identity
     return bases, exps, bits
 
 
@@ -36,26 +42,28 @@ def _words(bits):
     return np.array(w, dtype=np.uint64)
 
 
-def _worker(rank, world, port, seed, nbases, use_density, q):
+def _worker(rank, world, port, seed, nbases, use_density, q, ident=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     G = curves.Dummy
-    bases, exps, bits = _case(seed, nbases=nbases)
+    bases, exps, bits = _case(seed, nbases=nbases, ident=ident)
     words = _words(bits) if use_density else None
 
-    def partial_fn(lo, hi, first_base, dens_slice):
+    def partial_fn(lo, hi, first_base, dens_slice, n_total):
+        # what bmpc_multiexp_shard_dev hands back: the slice's partial sum + its raw flag word
+        dbits = [True] * (hi - lo)
+        if dens_slice is not None:
+            dbits = [bool((int(dens_slice[i // 64]) >> (i % 64)) & 1) for i in range(hi - lo)]
+        flags = ome.shard_flags(G, bases, first_base, dbits, exps[lo:hi], n_total, num_bits=16)
+        if flags:
+            return _lib.OK, flags, bytes(4)
         d = ome.FullDensity()
         if dens_slice is not None:
             d = ome.DensityTracker()
-            d.bv = [bool((int(dens_slice[i // 64]) >> (i % 64)) & 1) for i in range(hi - lo)]
-        try:
-            v = ome.multiexp(G, bases, first_base, d, exps[lo:hi], num_bits=16)
-            return _lib.OK, int(v).to_bytes(4, "little")
-        except ome.UnexpectedEof:
-            return _lib.ERR_UNEXPECTED_EOF, bytes(4)
-        except ome.UnexpectedIdentity:
-            return _lib.ERR_UNEXPECTED_IDENTITY, bytes(4)
+            d.bv = dbits
+        v = ome.multiexp(G, bases, first_base, d, exps[lo:hi], num_bits=16)
+        return _lib.OK, 0, int(v).to_bytes(4, "little")
 
     fold = lambda parts: sum(int.from_bytes(p, "little") for p in parts) % P
     st, res = bdist.sharded_multiexp(partial_fn, fold, len(exps), words, 3 if use_density else 0)
@@ -63,10 +71,10 @@ def _worker(rank, world, port, seed, nbases, use_density, q):
     dist.destroy_process_group()
 
 
-def _run(seed, nbases, use_density, port):
+def _run(seed, nbases, use_density, port, ident=None):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, seed, nbases, use_density, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, seed, nbases, use_density, q, ident)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(2)]
@@ -94,6 +102,64 @@ def test_sharded_matches_single(use_density):
 def test_sharded_eof_propagates():
     res = _run(6, 20, True, 29517)            # far too few bases: the upper rank overruns
     assert all(r[1] == _lib.ERR_UNEXPECTED_EOF for r in res)
+
+
+def _whole_status(seed, nbases, ident):
+    bases, exps, bits = _case(seed, nbases=nbases, ident=ident)
+    d = ome.DensityTracker()
+    d.bv = bits
+    try:
+        ome.multiexp(curves.Dummy, bases, 3, d, exps, num_bits=16)
+        return _lib.OK
+    except ome.UnexpectedEof:
+        return _lib.ERR_UNEXPECTED_EOF
+    except ome.UnexpectedIdentity:
+        return _lib.ERR_UNEXPECTED_IDENTITY
+
+
+@pytest.mark.parametrize("exp,port", [(0x3abc, 29521), (0x0abc, 29523), (1, 29525), (0, 29527)])
+def test_identity_on_lower_rank_vs_overrun_on_upper_rank(exp, port):
+    """multiexp.rs:244-249: the error reported is the first one, in scan order, of the HIGHEST failing
+    window.  Rank 1 overruns the bases (fails every window); rank 0 holds an identity base whose
+    exponent has a non-zero digit in the reference's top window (0x3abc, window 12..17 of c = 6 for
+    n = 203) -> UnexpectedIdentity; a zero top digit (0x0abc), exponent 1 (consumed in window 0 only)
+    -> UnexpectedEof; exponent 0 never looks at the base -> UnexpectedEof."""
+    ident = (5, exp)
+    nbases = 60                                   # rank 0's ~61 dense positions fit, rank 1 overruns
+    expect = _whole_status(7, nbases, ident)
+    assert expect == (_lib.ERR_UNEXPECTED_IDENTITY if exp == 0x3abc else _lib.ERR_UNEXPECTED_EOF)
+    res = _run(7, nbases, True, port, ident)
+    assert [r[1] for r in res] == [expect, expect]
+
+
+def test_shard_flags_reproduce_the_whole_multiexp_status():
+    """OR of the shards' flag words -> status == the oracle's multiexp over the whole vector, for
+    random placements of identity bases and overruns, worlds 1..4 (CPU, no processes)."""
+    G = curves.Dummy
+    rng = random.Random(11)
+    for trial in range(300):
+        n = rng.randrange(1, 120)
+        bits = [rng.random() < 0.7 for _ in range(n)]
+        nb = max(1, sum(bits) + rng.choice([-7, -1, 0, 3]))
+        bases = [rng.choice([0, rng.randrange(1, P)]) if rng.random() < 0.1 else rng.randrange(1, P) for _ in range(nb)]
+        exps = [rng.choice([0, 1, rng.randrange(P), rng.randrange(1 << 10)]) for _ in range(n)]
+        d = ome.DensityTracker()
+        d.bv = bits
+        try:
+            ome.multiexp(G, bases, 0, d, exps, num_bits=16)
+            expect = None
+        except ome.UnexpectedEof:
+            expect = "eof"
+        except ome.UnexpectedIdentity:
+            expect = "identity"
+        for world in (1, 2, 3, 4):
+            acc = 0
+            for r in range(world):
+                lo, hi = bdist.shard_range(n, world, r)
+                acc |= ome.shard_flags(G, bases, sum(bits[:lo]), bits[lo:hi], exps[lo:hi], n, num_bits=16)
+            assert ome.flags_status(acc) == expect, (trial, world)
+            want = {None: _lib.OK, "eof": _lib.ERR_UNEXPECTED_EOF, "identity": _lib.ERR_UNEXPECTED_IDENTITY}[expect]
+            assert bdist.flags_status(acc) == want
 
 
 def test_slicing_helpers():

@@ -189,6 +189,52 @@ def test_error_semantics(worker):
     assert _error_case(worker, p1, 0, None, s6) == "identity"
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_error_precedence_across_shards(worker, world):
+    """multiexp.rs:244-249 over a sharded multiexp: the shards run one after the other on
+    this GPU through bmpc_multiexp_shard_dev, each against ITS slice of the bases; the OR of their
+    raw flag words must give the status the oracle's multiexp reports for the whole vector.  The
+    reference's window is c = ceil(ln 70) = 5 (top window = bits 250..254); a shard of 35 or 24
+    exponents alone would take c = 4 (bits 252..255) and misjudge the digit 1 << 250."""
+    import ctypes as C
+    import torch
+    from bellman_mpc_b200 import dist as bdist
+    G = curves.G1
+    rng = random.Random(91)
+    n, nbases = 70, 60
+    pts = [G.mul(G.gen, rng.randrange(1, Q)) for _ in range(nbases)]
+    pts[3] = None                                                    # identity base on shard 0
+    base_sc = [rng.randrange(Q) for _ in range(n)]
+    lib = worker._lib
+    for s3, want in (((1 << 250) + 9, "identity"), ((1 << 249) + 9, "eof"), (1, "eof"), (0, "eof")):
+        sc = list(base_sc)
+        sc[3] = s3
+        try:
+            ome.multiexp(G, pts, 0, ome.FullDensity(), sc)
+            exp = "ok"
+        except ome.UnexpectedIdentity:
+            exp = "identity"
+        except ome.UnexpectedEof:
+            exp = "eof"
+        assert exp == want
+        acc = 0
+        for r in range(world):
+            lo, hi = bdist.shard_range(n, world, r)
+            sl = pts[lo:min(hi, nbases)]                              # the rank's slice of the bases
+            bases = bm.Bases.from_uncompressed(worker, bm.G1, b"".join(G.to_uncompressed(p) for p in sl)) if sl else \
+                bm.Bases.from_uncompressed(worker, bm.G1, b"", 0)
+            d_sc = torch.from_numpy(bm.ints_to_limbs(sc[lo:hi]).view(np.int64)).cuda()
+            part = torch.zeros(int(lib.bmpc_partial_bytes(bm.G1)), dtype=torch.uint8, device="cuda")
+            fl = C.c_uint32(0)
+            rc = lib.bmpc_multiexp_shard_dev(worker.ctx, bases.handle, 0, d_sc.data_ptr(), hi - lo, None, 0, n,
+                                             part.data_ptr(), C.byref(fl), None)
+            assert rc == 0
+            acc |= fl.value
+            bases.free()
+        got = {0: "ok", 1: "identity", 2: "eof"}[lib.bmpc_msm_flags_status(acc)]
+        assert got == exp == {0: "ok", 1: "identity", 2: "eof"}[bdist.flags_status(acc)]
+
+
 @pytest.mark.parametrize("group,n,c", [(bm.G1, 5000, 0), (bm.G1, 3000, 9), (bm.G2, 1500, 0), (bm.G1, 1 << 16, 0)])
 def test_precomputed_tables(worker, group, n, c):
     """window tables 2^(cw) P_i (one bucket set, no doubling fold) give the same bytes, also with
@@ -341,5 +387,11 @@ def test_list_mul_matrix(worker):
         bm.list_mul_matrix(s1, s2, [[(1, 12)]])
     with pytest.raises(AssertionError):
         bm.list_mul_matrix(s1, s2, [[(1, 0)]] * 13)
+    # a matrix TALLER than the list whose first empty row comes before row list.len() is fine in the
+    # reference (the loop breaks there, mpc.rs:432-434) -- and here
+    tall = [[(3, 1)], [(5, 2)], []] + [[(1, 0)]] * 20
+    t1, t2 = bm.list_mul_matrix(s1, s2, tall)
+    assert t1.read() == b"".join(G.to_uncompressed(p) for p in ompc.list_mul_matrix(G, lst, tall))
+    t1.free(); t2.free()
     for b in (b1, b2, r1, r2, s1, s2, o1, o2, e1, e2):
         b.free()

@@ -34,6 +34,35 @@ def test_transforms_bit_exact(worker, logn):
         assert got == o.coeffs, (logn, name)
 
 
+def _rand_mont(m, seed):
+    """m x 4 u64, uniform below 2^254 (< q): valid fully reduced Montgomery residues"""
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 1 << 63, size=(m, 4), dtype=np.int64).astype(np.uint64)
+    a[:, 3] >>= np.uint64(1)
+    return a
+
+
+@pytest.mark.parametrize("logn", [16, 18, 20, 22, 24, 26])
+def test_transforms_bit_exact_sweep(worker, logn):
+    """BASELINE config #3: fft / ifft / coset_fft / icoset_fft over 2^16 .. 2^26, every limb of every
+    coefficient equal to the C restatement of domain.rs:81-125,261-372 (oracle/c, itself pinned to the
+    Python oracle and through it to the reference's known answers).  2^26 is the 4-pass transform
+    with the two-level twiddle lookup (direct power tables end at 2^24)."""
+    import ctypes as C
+    from oracle import cref
+    m = 1 << logn
+    coeffs = _rand_mont(m, 500 + logn)
+    threads = cref.hardware_threads()
+    lib = worker._lib
+    for op in (bm.FFT, bm.IFFT, bm.COSET_FFT, bm.ICOSET_FFT):
+        want = cref.ntt(coeffs, op, threads=threads)
+        got = coeffs.copy()
+        rc = lib.bmpc_ntt(worker.ctx, got.ctypes.data_as(C.c_void_p), logn, op)
+        assert rc == 0
+        assert np.array_equal(got, want), (logn, op, int((got != want).any(axis=1).sum()))
+        del want, got
+
+
 @pytest.mark.parametrize("maxdeg", [3, 5, 10])
 def test_pass_split_consistency(worker, maxdeg):
     """parallel_fft_consistency analogue: the result must not depend on how the transform is
