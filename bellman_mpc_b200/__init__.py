@@ -119,6 +119,10 @@ class Worker:
     def set_tuning(self, msm_window_bits=0, ntt_max_deg=0):
         _raise(self._lib.bmpc_ctx_set_tuning(self.ctx, msm_window_bits, ntt_max_deg), self.ctx)
 
+    def reload_env(self):
+        """re-read the BMPC_* tuning variables (they are parsed once per context otherwise)"""
+        _raise(self._lib.bmpc_ctx_reload_env(self.ctx), self.ctx)
+
     def launch_count(self):
         return int(self._lib.bmpc_ctx_launch_count(self.ctx))
 

@@ -20,7 +20,7 @@ FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
 # every symbol include/bellman_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "bmpc_ctx_create", "bmpc_ctx_destroy", "bmpc_last_error", "bmpc_ctx_set_tuning",
-    "bmpc_ctx_launch_count", "bmpc_ctx_profile", "bmpc_ctx_profile_read",
+    "bmpc_ctx_reload_env", "bmpc_ctx_launch_count", "bmpc_ctx_profile", "bmpc_ctx_profile_read",
     "bmpc_bases_register", "bmpc_bases_register_dev", "bmpc_bases_precompute", "bmpc_bases_len", "bmpc_bases_group",
     "bmpc_bases_read", "bmpc_bases_dev_ptr", "bmpc_bases_free",
     "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_multiexp_shard_dev",
@@ -95,6 +95,7 @@ def load():
         "bmpc_ctx_destroy": (None, [vp]),
         "bmpc_last_error": (C.c_char_p, [vp]),
         "bmpc_ctx_set_tuning": (i32, [vp, i32, i32]),
+        "bmpc_ctx_reload_env": (i32, [vp]),
         "bmpc_ctx_launch_count": (C.c_uint64, [vp]),
         "bmpc_ctx_profile": (i32, [vp, i32]),
         "bmpc_ctx_profile_read": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -135,6 +135,26 @@ int register_points(bmpc_ctx* ctx, bmpc_bases* b, cudaStream_t st) {
 
 }  // namespace
 
+void bmpc_tuning::load() {
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    acc_pairs = geti("BMPC_ACC_PAIRS", -1);
+    const char* me = getenv("BMPC_PAIR_MIN_ENTRIES");
+    pair_min_entries = me ? (size_t)atoll(me) : ((size_t)1 << 22);
+    pair_k = geti("BMPC_PAIR_K", 0);
+    acc_affine = geti("BMPC_ACC_AFFINE", -1);
+    aff_blockdim = geti("BMPC_AFF_BLOCKDIM", 0);
+    aff_ksel = geti("BMPC_AFF_KSEL", 0);
+    aff_minb = geti("BMPC_AFF_MINB", 0);
+    aff_gmax = geti("BMPC_AFF_GMAX", 0);
+    aff_waves = geti("BMPC_AFF_WAVES", 0);
+    aff_force_g = geti("BMPC_AFF_FORCE_G", 0);
+    aff_whole_waves = geti("BMPC_AFF_WHOLE_WAVES", 1);
+    acc_compact = geti("BMPC_ACC_COMPACT", 0);
+    subwindows = geti("BMPC_MSM_SUBWINDOWS", 1);
+    reduce_block = geti("BMPC_REDUCE_BLOCK", 0);
+    ntt_no_direct = geti("BMPC_NTT_NO_DIRECT", 0);
+}
+
 // =============================================================================== C ABI
 extern "C" {
 
@@ -152,6 +172,7 @@ int bmpc_ctx_create(int device, bmpc_ctx** out) {
         delete ctx;
         return BMPC_ERR_CUDA;
     }
+    ctx->tune.load();
     const char* ec = getenv("BMPC_MSM_WINDOW");
     if (ec) ctx->tune_c = atoi(ec);
     const char* ed = getenv("BMPC_NTT_MAXDEG");
@@ -189,6 +210,13 @@ int bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->tune_c = msm_window_bits;
     ctx->tune_maxdeg = ntt_max_deg;
+    return BMPC_OK;
+}
+
+int bmpc_ctx_reload_env(bmpc_ctx* ctx) {
+    if (!ctx) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->tune.load();
     return BMPC_OK;
 }
 
@@ -362,8 +390,9 @@ int bmpc_msm_accumulate_info(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, u
     if (bases->group == BMPC_G1) GroupOps<Fp>::plan_affine(ctx, p);
     else GroupOps<Fp2>::plan_affine(ctx, p);
     for (int i = 0; i < 8; i++) info[i] = 0;
-    info[0] = p.affine ? 1u : 0u;
+    info[0] = p.pairs ? 2u : (p.affine ? 1u : 0u);
     info[1] = p.aff_G; info[2] = p.aff_K; info[3] = p.aff_blocks; info[4] = p.aff_block; info[5] = p.g.L;
+    if (p.pairs) { info[1] = p.pair_R; info[2] = p.pair_kmax; info[3] = p.pair_blocks; info[4] = p.pair_block; }
     return BMPC_OK;
 }
 

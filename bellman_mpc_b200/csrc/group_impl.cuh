@@ -6,6 +6,7 @@
 #include "internal.h"
 #include "group_kernels.cuh"
 #include "msm_affine.cuh"
+#include "msm_pairs.cuh"
 
 namespace bmpc {
 
@@ -28,14 +29,94 @@ static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb, uint32_t blk = 128) {
     return minb == 4 ? msm_accumulate_affine_kernel<F, 128, 4> : msm_accumulate_affine_kernel<F, 128, 1>;
 }
 
+// ---- round-based pair accumulation (msm_pairs.cuh) -------------------------------------------
+template <class F>
+struct PairCfg;
+template <>
+struct PairCfg<Fp> {       // 61 KB of staging per block: three 128-thread blocks per SM at <= 168 registers
+    static constexpr int BLK = 128, MINB = 3;
+    static constexpr bool PK = true;
+};
+template <>
+struct PairCfg<Fp2> {      // 96 KB of staging per block (prefix product read directly): two blocks per SM
+    static constexpr int BLK = 128, MINB = 2;
+    static constexpr bool PK = false;
+};
+template <class F>
+static size_t pair_smem_bytes() {
+    typedef PairStage<F, PairCfg<F>::BLK, PairCfg<F>::PK> Stage;
+    size_t tree = 4 * (size_t)PairCfg<F>::BLK * sizeof(F);
+    return Stage::BYTES > tree ? Stage::BYTES : tree;
+}
+template <class F, bool R0>
+static void (*pair_kernel())(PairArgs<F>) {
+    return msm_pair_round_kernel<F, R0, PairCfg<F>::BLK, PairCfg<F>::MINB, PairCfg<F>::PK>;
+}
+
+// Decides whether this multiexp accumulates its buckets in pair rounds and lays the rounds out.
+// BMPC_ACC_PAIRS = 0 never, 1 always (tests run every accumulate kernel on the same inputs); default:
+// from BMPC_PAIR_MIN_ENTRIES (position, window) entries up, where the rounds fill the GPU.
+template <class F>
+static bool plan_pairs(bmpc_ctx* ctx, MsmPlan& p) {
+    const int mode = ctx->tune.acc_pairs;
+    const size_t min_entries = ctx->tune.pair_min_entries;
+    const uint32_t kmax_env = ctx->tune.pair_k > 0 ? (uint32_t)ctx->tune.pair_k : 0;
+    if (mode == 0) return false;
+    if (mode != 1 && p.max_pairs < min_entries) return false;
+    // slices of at most L = 2^R entries, L >= twice the mean bucket (most buckets are one slice)
+    size_t avg = p.max_pairs / (p.nb ? p.nb : 1);
+    uint32_t R = 6;
+    while (R < BMPC_PAIR_MAX_ROUNDS && ((size_t)1 << R) < 2 * avg) R++;
+    MsmPlan q = p;
+    q.pairs = true;
+    q.g.L = 1u << R;
+    q.pair_R = R;
+    msm_plan_sizes(q);
+    const size_t entries = q.max_pairs + q.nb;               // padded entry bound
+    size_t ob = 0, lo = 0;
+    for (uint32_t r = 0; r <= R; r++) {
+        q.pair_out[r] = (uint32_t)ob;
+        q.pair_list[r] = (uint32_t)lo;
+        size_t pmax = r == 0 ? entries / 2 + 1 : (entries >> (r + 1)) + q.max_tasks + 1;
+        ob += pmax;
+        if (r >= 1) lo += pmax;
+        if (ob >= ((size_t)1 << 32) - 1) return false;       // pool indices are 32-bit
+    }
+    int sms = 148, occ = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t smem = pair_smem_bytes<F>();
+    cudaFuncSetAttribute(pair_kernel<F, true>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(pair_kernel<F, false>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pair_kernel<F, true>(), PairCfg<F>::BLK, smem);
+    if (occ < 1) return false;
+    q.pair_block = PairCfg<F>::BLK;
+    q.pair_minb = (uint32_t)occ;
+    q.pair_blocks = (uint32_t)(sms * occ);
+    q.pair_kmax = kmax_env ? kmax_env : 256;
+    q.pair_stride = (uint32_t)align_up(q.max_tasks, 64);
+    q.pair_cstride = (uint32_t)align_up((q.max_tasks + 1023) / 1024 + 2, 64);   // scan chunks of 1024 tasks
+    q.affine = false;
+    p = q;
+    return true;
+}
+template <class F>
+static size_t pair_bytes(const MsmPlan& p) {
+    const uint32_t R = p.pair_R;
+    return ws_need(p.pair_out[R], sizeof(Affine<F>)) + ws_need((size_t)p.pair_list[R] + 1, 8) +
+           ws_need((size_t)(R ? R - 1 : 0) * p.pair_stride + 1, 4) + ws_need((size_t)(R ? R - 1 : 0) * p.pair_cstride + 1, 4) +
+           ws_need(64, 4) + ws_need(p.max_tasks, 4) +
+           ws_need((size_t)p.pair_blocks * p.pair_block * p.pair_kmax, sizeof(F));
+}
+
 // Batched-affine accumulation pays when there are enough bucket slices to give every resident
 // thread a job of >= 2 slices (fewer: the inversion is not amortised and the XYZZ kernel wins).
 // BMPC_ACC_AFFINE=0 disables it, =1 forces it (tests run both paths on the same inputs).
 template <class F>
 void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
-    const char* e = getenv("BMPC_ACC_AFFINE");
-    int mode = e ? atoi(e) : -1;
+    const bmpc_tuning& tn = ctx->tune;
+    int mode = tn.acc_affine;
     p.affine = false;
+    if (plan_pairs<F>(ctx, p)) return;
     if (mode == 0) return;
     int sms = 148, occ = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -45,17 +126,17 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     // block per SM pays only for the largest bucket sets (2^24: 57.86 ms, but 2^21: 9.43 ms).
     // G2 stays at 128 (168 registers, 3 blocks per SM).
     uint32_t blk = sizeof(F) == sizeof(Fp) ? (p.nb >= (1u << 21) ? 512 : 256) : 128;
-    if (getenv("BMPC_AFF_BLOCKDIM")) {
-        uint32_t v = (uint32_t)atoi(getenv("BMPC_AFF_BLOCKDIM"));
+    if (tn.aff_blockdim) {
+        uint32_t v = (uint32_t)tn.aff_blockdim;
         if (v == 32 || v == 64 || v == 128 || ((v == 256 || v == 512) && sizeof(F) == sizeof(Fp))) blk = v;
     }
     // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
     // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 at 2^22: 168 registers (3 blocks per
     // SM, 0.9 KB of spills) 60.3 ms, 252 registers (2 blocks) 65.0 ms, XYZZ kernel 72.0 ms.
-    p.aff_K = (getenv("BMPC_AFF_KSEL") && atoi(getenv("BMPC_AFF_KSEL")) == 128) ? 128 : 384;
+    p.aff_K = tn.aff_ksel == 128 ? 128 : 384;
     p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 3;
-    if (getenv("BMPC_AFF_MINB")) {
-        int v = atoi(getenv("BMPC_AFF_MINB"));
+    if (tn.aff_minb) {
+        int v = tn.aff_minb;
         p.aff_minb = (v == 4 || v == 3) ? (uint32_t)v : 1u;
     }
     p.aff_block = blk;
@@ -66,8 +147,7 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     if (occ < 1) occ = 1;
     size_t resident = (size_t)sms * occ * blk;
     size_t gmax = BMPC_AFF_G;                      // BMPC_AFF_GMAX: tuning knob (slices per job)
-    if (getenv("BMPC_AFF_GMAX") && atoi(getenv("BMPC_AFF_GMAX")) >= 1 && (size_t)atoi(getenv("BMPC_AFF_GMAX")) < gmax)
-        gmax = (size_t)atoi(getenv("BMPC_AFF_GMAX"));
+    if (tn.aff_gmax >= 1 && (size_t)tn.aff_gmax < gmax) gmax = (size_t)tn.aff_gmax;
     // Slices per job.  Jobs are handed out in waves of `resident` threads; with a single wave the
     // kernel's second half runs on a half-empty GPU (threads finish at different times and nothing
     // refills them), so G is chosen among the values that give at least TWO waves, maximising the
@@ -78,10 +158,10 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     // BMPC_AFF_WHOLE_WAVES (default on): the kernel deals the slices over a whole number of waves
     // (njobs = waves x resident threads), so the fill of the last wave no longer depends on G and G
     // only sets the amortisation: the largest G <= gmax that still leaves two waves.
-    p.aff_whole_waves = !(getenv("BMPC_AFF_WHOLE_WAVES") && atoi(getenv("BMPC_AFF_WHOLE_WAVES")) == 0);
+    p.aff_whole_waves = tn.aff_whole_waves != 0;
     if (p.aff_whole_waves) {
         size_t per_thread = (p.nb + resident - 1) / resident;      // slices per resident thread
-        size_t waves = getenv("BMPC_AFF_WAVES") && atoi(getenv("BMPC_AFF_WAVES")) >= 1 ? (size_t)atoi(getenv("BMPC_AFF_WAVES")) : 2;
+        size_t waves = tn.aff_waves >= 1 ? (size_t)tn.aff_waves : 2;
         G = (per_thread + waves - 1) / waves;                       // `waves` (2) waves of jobs this size
         if (G > gmax) G = gmax;
         if (G < 2) G = 2;
@@ -98,7 +178,7 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     // tables: 18.1 vs 20.1 ms at 2^22, 31.3 vs 36.8 at 2^23, 59.5 vs 73.2 at 2^24; G2 69.7 vs 74.4 at 2^22).
     if (G < 2) {
         if (mode != 1) return;
-        G = getenv("BMPC_AFF_FORCE_G") ? (size_t)atoi(getenv("BMPC_AFF_FORCE_G")) : 2;
+        G = tn.aff_force_g ? (size_t)tn.aff_force_g : 2;
         if (G < 1) G = 1;
         if (G > BMPC_AFF_G) G = BMPC_AFF_G;
     }
@@ -114,6 +194,7 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
 
 template <class F>
 size_t GroupOps<F>::curve_bytes(const MsmPlan& p) {
+    if (p.pairs) return curve_bytes_xyzz(p) + pair_bytes<F>(p);
     if (p.affine)
         return curve_bytes_xyzz(p) + ws_need((size_t)p.aff_blocks * p.aff_block * p.aff_G * (p.aff_HA + p.aff_HB), sizeof(Affine<F>));
     return curve_bytes_xyzz(p);
@@ -145,7 +226,40 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     }
     const Affine<F>* pts = reinterpret_cast<const Affine<F>*>(bases->d_points);
     uint32_t ablocks = (uint32_t)((p.max_tasks + 127) / 128);
-    if (p.affine) {
+    if (p.pairs) {
+        const uint32_t R = p.pair_R;
+        Affine<F>* pool = ws_take<Affine<F>>(ctx, p.pair_out[R]);
+        uint2* lists = ws_take<uint2>(ctx, (size_t)p.pair_list[R] + 1);
+        uint32_t* pairoff = ws_take<uint32_t>(ctx, (size_t)(R - 1) * p.pair_stride + 1);
+        uint32_t* csums = ws_take<uint32_t>(ctx, (size_t)(R - 1) * p.pair_cstride + 1);
+        uint32_t* totals = ws_take<uint32_t>(ctx, 64);
+        uint32_t* fin = ws_take<uint32_t>(ctx, p.max_tasks);
+        F* pre = ws_take<F>(ctx, (size_t)p.pair_blocks * p.pair_block * p.pair_kmax);
+        if (!pool || !lists || !pairoff || !csums || !totals || !fin || !pre) {
+            ctx->err = "msm workspace carve failed (pair rounds)";
+            return BMPC_ERR_INVALID;
+        }
+        ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
+        // per-round task scans -> dense pair lists of rounds 1 .. R-1 (msm_sort.cu)
+        int rcp = msm_pairs_prepare(ctx, p, s, csums, totals, pairoff, lists, fin, st);
+        if (rcp) return rcp;
+        const size_t smem = pair_smem_bytes<F>();
+        for (uint32_t r = 0; r < R; r++) {
+            PairArgs<F> a;
+            a.tables = pts;
+            a.out = pool;
+            a.list = r == 0 ? reinterpret_cast<const uint2*>(s.sorted) : lists + p.pair_list[r];
+            a.count_p = r == 0 ? s.nsorted : totals + r;
+            a.count_shift = r == 0 ? 1u : 0u;
+            a.out_base = p.pair_out[r];
+            a.pre = pre;
+            a.kmax = p.pair_kmax;
+            if (r == 0) LAUNCH(ctx, (pair_kernel<F, true>()), p.pair_blocks, p.pair_block, smem, st, a);
+            else LAUNCH(ctx, (pair_kernel<F, false>()), p.pair_blocks, p.pair_block, smem, st, a);
+        }
+        LAUNCH(ctx, msm_pair_collect_kernel<F>, ablocks, 128, 0, st, (const Affine<F>*)pool, (const uint32_t*)fin,
+               s.desc, s.ntasks, partials);
+    } else if (p.affine) {
         Affine<F>* scratch = ws_take<Affine<F>>(ctx, (size_t)p.aff_blocks * p.aff_block * p.aff_G * (p.aff_HA + p.aff_HB));
         if (!scratch) {
             ctx->err = "msm workspace carve failed (affine scratch)";
@@ -159,7 +273,7 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     } else {
         ProfScope ps(ctx, BMPC_PROF_MSM_ACCUMULATE, st);
         // BMPC_ACC_COMPACT=1 selects the variant whose field products are calls (smaller code)
-        static const bool compact = getenv("BMPC_ACC_COMPACT") && atoi(getenv("BMPC_ACC_COMPACT")) != 0;
+        const bool compact = ctx->tune.acc_compact != 0;
         if (compact)
             LAUNCH(ctx, (msm_accumulate_kernel<F, true>), ablocks, 128, 0, st, pts, s.sorted, s.desc, s.ntasks, partials);
         else

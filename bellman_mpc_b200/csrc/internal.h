@@ -39,8 +39,25 @@ struct DomainTables {
 
 }  // namespace bmpc
 
+// Tuning knobs read from BMPC_* environment variables ONCE per context (bmpc_ctx_create) and again on
+// bmpc_ctx_reload_env -- not per call.  -1 / 0 = automatic unless noted.
+struct bmpc_tuning {
+    int acc_pairs = -1;            // BMPC_ACC_PAIRS: 0 never, 1 always pair rounds (msm_pairs.cuh)
+    size_t pair_min_entries = (size_t)1 << 22;   // BMPC_PAIR_MIN_ENTRIES
+    int pair_k = 0;                // BMPC_PAIR_K: pairs per thread per inversion
+    int acc_affine = -1;           // BMPC_ACC_AFFINE: 0 never, 1 always the batched-affine tree
+    int aff_blockdim = 0, aff_ksel = 0, aff_minb = 0, aff_gmax = 0, aff_waves = 0, aff_force_g = 0;
+    int aff_whole_waves = 1;
+    int acc_compact = 0;           // BMPC_ACC_COMPACT
+    int subwindows = 1;            // BMPC_MSM_SUBWINDOWS
+    int reduce_block = 0;          // BMPC_REDUCE_BLOCK
+    int ntt_no_direct = 0;         // BMPC_NTT_NO_DIRECT
+    void load();
+};
+
 struct bmpc_ctx {
     int device = 0;
+    bmpc_tuning tune;
     std::string err;
     std::mutex mu;
     uint64_t launches = 0;
@@ -270,8 +287,20 @@ struct MsmPlan {
     // batched-affine accumulation (msm_affine.cuh): decided per group in GroupOps::plan_affine
     bool affine = false, aff_whole_waves = false;
     uint32_t aff_G = 0, aff_blocks = 0, aff_block = 128, aff_K = 128, aff_minb = 1, aff_HA = 0, aff_HB = 0;
+    // round-based pair accumulation (msm_pairs.cuh): decided per group in GroupOps::plan_affine.
+    // pair_R rounds (slices of at most 2^pair_R entries, every bucket padded to an even count),
+    // pair_out[r] / pair_list[r]: first pool index / first list entry of round r (host-side bounds)
+    bool pairs = false;
+    uint32_t pair_R = 0, pair_blocks = 0, pair_block = 128, pair_minb = 3, pair_kmax = 256;
+    uint32_t pair_out[16] = {0}, pair_list[16] = {0};
+    uint32_t pair_stride = 0, pair_cstride = 0;   // row pitch of the per-round task scans / their chunk sums
+    size_t n = 0;
+    bool has_density = false;
     size_t sort_bytes;  // scratch for everything except the curve-typed buffers
 };
+// (re)derives max_tasks and sort_bytes from g.L / pairs (called by msm_make_plan and again by
+// plan_affine when it switches the plan to pair rounds)
+void msm_plan_sizes(MsmPlan& p);
 
 struct MsmSorted {      // outputs of the sort stage (device pointers into the arena)
     uint32_t* sorted;   // base index | sign << 31, grouped by bucket
@@ -281,6 +310,7 @@ struct MsmSorted {      // outputs of the sort stage (device pointers into the a
     uint32_t* heavy_count;
     uint4* desc;        // per task {first sorted entry, length, partial slot, bucket}, big tasks first
     uint32_t* ntasks;   // device pointer to the task count (== toff[nb])
+    uint32_t* nsorted;  // device pointer to the number of entries in `sorted` (== off[nb]; padded in pair mode)
 };
 
 MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density, size_t n_ref = 0);
@@ -289,6 +319,11 @@ uint32_t msm_table_window(size_t n_bases);  // window bits used for precomputed 
 int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,
                  const uint32_t* d_scalars, size_t n, const uint32_t* d_density, uint32_t* d_flags,
                  MsmSorted* out, cudaStream_t st);
+
+// pair mode (msm_pairs.cuh): scans the tasks' pairs per round and writes the lists of rounds
+// 1 .. R-1 (uint2 pool indices) and every task's result index `fin`
+int msm_pairs_prepare(bmpc_ctx* ctx, const MsmPlan& p, const MsmSorted& s, uint32_t* csums, uint32_t* totals,
+                      uint32_t* pairoff, uint2* lists, uint32_t* fin, cudaStream_t st);
 
 // -------------------------------------------------- group_g1.cu / group_g2.cu
 template <class F>

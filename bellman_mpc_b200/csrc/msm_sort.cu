@@ -77,7 +77,7 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         // the table window minimising additions + 7 per bucket + the doublings' latency (one cold
         // doubling on the serial tail ~ 22 us ~ 6 10^4 accumulated points).
         double best = window_cost(n, bases->tab_c, true);
-        static const bool subw = !(getenv("BMPC_MSM_SUBWINDOWS") && atoi(getenv("BMPC_MSM_SUBWINDOWS")) == 0);
+        const bool subw = ctx->tune.subwindows != 0;
         for (uint32_t k = 2; k <= bases->tab_c / 2 && !ctx->tune_c && subw; k++) {
             if (bases->tab_c % k) continue;
             uint32_t cs = bases->tab_c / k;
@@ -97,13 +97,14 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     g.tab_stride = tables ? (uint32_t)bases->n : 0u;
     size_t avg = n * (g.W / g.H) / g.B;
     g.L = (uint32_t)(2 * avg < 64 ? 64 : 2 * avg);
+    p.n = n;
+    p.has_density = has_density;
     // the reference picks its window from the length of the whole exponent vector; a shard of a
     // larger multiexp passes that length so that "which error wins" is decided as the reference does
     g.c_ref = reference_window(n_ref > n ? n_ref : n);
     g.top_skip = (254 / g.c_ref) * g.c_ref;
     p.nb = g.H * g.B;
     p.max_pairs = n * g.W;
-    p.max_tasks = p.max_pairs / g.L + p.nb + 1;
     // reduce: each thread owns S = 2^s_log consecutive buckets of one set (msm_reduce_kernel), blocks
     // of 256 threads.  S is the smallest power of two for which all H sets fit in ONE wave of
     // resident blocks (a second, nearly empty wave doubles the kernel time; 2 resident 256-thread
@@ -124,8 +125,8 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         // kernel is latency-bound either way, and the extra fold levels and doublings cost more than
         // the smaller blocks save (measured per G2 multiexp of the 2^22 proof: 4.19 -> 4.70 ms).
         uint32_t rb = bases->group == BMPC_G1 ? 32 : 256;   // measured (G1, 2^19 buckets): 32 -> 2.38 ms, 64 -> 2.47, 128 -> 2.50, 256 -> 2.58 for combine + reduce + fold + final
-        if (getenv("BMPC_REDUCE_BLOCK")) {
-            uint32_t v = (uint32_t)atoi(getenv("BMPC_REDUCE_BLOCK"));
+        {
+            uint32_t v = (uint32_t)ctx->tune.reduce_block;
             if (v == 32 || v == 64 || v == 128 || v == 256) rb = v;
         }
         while (s_log < g.c - 1 && (g.B >> s_log) > rb * BMPC_FOLD_GROUP * 256u) s_log++;
@@ -134,16 +135,23 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         p.rblock = p.tpw < rb ? p.tpw : rb;
         p.nblk = p.tpw / p.rblock;
     }
+    msm_plan_sizes(p);
+    return p;
+}
+
+void msm_plan_sizes(MsmPlan& p) {
+    // pair mode pads every bucket to an even number of entries (one pad entry per odd bucket)
+    const size_t entries = p.max_pairs + (p.pairs ? p.nb : 0);
+    p.max_tasks = entries / p.g.L + p.nb + 1;
     size_t b = 0;
-    size_t nw32 = (n + 31) / 32;
-    if (has_density) b += ws_need(nw32 + 1, 4) * 2 + ws_need(scan_chunks_words((uint32_t)nw32), 4);
+    size_t nw32 = (p.n + 31) / 32;
+    if (p.has_density) b += ws_need(nw32 + 1, 4) * 2 + ws_need(scan_chunks_words((uint32_t)nw32), 4);
     b += ws_need(p.nb + 1, 4) * 5;  // hist, off, toff, cursor, heavy
     b += ws_need(scan_chunks_words(p.nb), 4);
-    b += ws_need(p.max_pairs + 1, 4);  // sorted
+    b += ws_need(entries + 2, 4);   // sorted
     b += ws_need(64, 4) + ws_need(256, 4);
     b += ws_need(p.max_tasks, 16);     // task descriptors
     p.sort_bytes = b + 4096;
-    return p;
 }
 
 // out[n+1] = exclusive scan of xform(in); `chunks` scratch of scan_chunks_words(n) words
@@ -191,7 +199,8 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     uint32_t* cursor = ws_take<uint32_t>(ctx, p.nb + 1);
     uint32_t* heavy = ws_take<uint32_t>(ctx, p.nb + 1);
     uint32_t* chunks = ws_take<uint32_t>(ctx, scan_chunks_words(p.nb));
-    uint32_t* sorted = ws_take<uint32_t>(ctx, p.max_pairs + 1);
+    const size_t sorted_entries = p.max_pairs + (p.pairs ? p.nb : 0) + 2;
+    uint32_t* sorted = ws_take<uint32_t>(ctx, sorted_entries);
     uint32_t* heavy_count = ws_take<uint32_t>(ctx, 64);
     uint32_t* bins = ws_take<uint32_t>(ctx, 256);
     uint4* desc = ws_take<uint4>(ctx, p.max_tasks);
@@ -207,8 +216,10 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     CK(cudaMemsetAsync(heavy_count, 0, 4, st));
     uint32_t nblocks = (uint32_t)((n + 255) / 256);
     LAUNCH(ctx, msm_count_kernel, nblocks, 256, 0, st, in, g, hist, d_flags);
-    int rc = run_scan(ctx, hist, p.nb, 0, chunks, off, st);
+    // pair mode: bucket offsets with every count rounded up to even, the pad slots keep BMPC_PAIR_PAD
+    int rc = run_scan(ctx, hist, p.nb, p.pairs ? BMPC_SCAN_EVEN : 0, chunks, off, st);
     if (rc) return rc;
+    if (p.pairs) CK(cudaMemsetAsync(sorted, 0xff, sorted_entries * 4, st));
     rc = run_scan(ctx, hist, p.nb, g.L, chunks, toff, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(cursor, off, (size_t)p.nb * 4, cudaMemcpyDeviceToDevice, st));
@@ -225,6 +236,28 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     out->toff = toff;
     out->heavy = heavy;
     out->heavy_count = heavy_count;
+    out->nsorted = off + p.nb;
+    return BMPC_OK;
+}
+
+int msm_pairs_prepare(bmpc_ctx* ctx, const MsmPlan& p, const MsmSorted& s, uint32_t* csums, uint32_t* totals,
+                      uint32_t* pairoff, uint2* lists, uint32_t* fin, cudaStream_t st) {
+    const uint32_t R = p.pair_R;
+    static_assert(BMPC_SCAN_CHUNK == 1024, "pair_cstride assumes scan chunks of 1024 tasks");
+    const uint32_t nchunks = (uint32_t)((p.max_tasks + BMPC_SCAN_CHUNK - 1) / BMPC_SCAN_CHUNK);
+    dim3 sgrid(nchunks, R - 1);
+    LAUNCH(ctx, pair_scan_phase1_kernel, sgrid, BMPC_SCAN_THREADS, 0, st, s.desc, s.ntasks, csums, p.pair_cstride);
+    LAUNCH(ctx, pair_scan_phase2_kernel, R - 1, BMPC_SCAN_THREADS, 0, st, csums, p.pair_cstride, nchunks, totals);
+    LAUNCH(ctx, pair_scan_phase3_kernel, sgrid, BMPC_SCAN_THREADS, 0, st, s.desc, s.ntasks, (const uint32_t*)csums,
+           p.pair_cstride, pairoff, p.pair_stride);
+    PairLayout lay;
+    lay.R = R;
+    for (uint32_t r = 0; r <= BMPC_PAIR_MAX_ROUNDS; r++) {
+        lay.out_base[r] = r <= R ? p.pair_out[r] : 0;
+        lay.list_off[r] = r <= R ? p.pair_list[r] : 0;
+    }
+    LAUNCH(ctx, pair_build_kernel, (uint32_t)((p.max_tasks + 127) / 128), 128, 0, st, s.desc, s.ntasks, lay,
+           (const uint32_t*)pairoff, p.pair_stride, lists, fin);
     return BMPC_OK;
 }
 

@@ -2,6 +2,7 @@
 // (stages 1-3 of the pipeline described in group_kernels.cuh).
 #pragma once
 #include "internal.h"
+#include "msm_pair_lists.h"
 
 namespace bmpc {
 
@@ -148,7 +149,9 @@ __global__ void popc_words_kernel(const uint32_t* words, uint32_t nwords, uint32
 #define BMPC_SCAN_ITEMS 4
 #define BMPC_SCAN_CHUNK (BMPC_SCAN_THREADS * BMPC_SCAN_ITEMS)
 
+#define BMPC_SCAN_EVEN 0xffffffffu       // scan x rounded up to even (pair mode bucket offsets)
 __device__ __forceinline__ uint32_t scan_xform(uint32_t x, uint32_t L) {
+    if (L == BMPC_SCAN_EVEN) return x + (x & 1u);
     return L ? (x + L - 1u) / L : x;
 }
 
@@ -296,6 +299,80 @@ __global__ void msm_find_heavy_kernel(const uint32_t* toff, uint32_t nb, uint32_
     if (b >= nb) return;
     // up to BMPC_INLINE_PARTIALS partial sums are folded by the reduce kernel itself
     if (toff[b + 1] - toff[b] > BMPC_INLINE_PARTIALS) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+}
+
+// ============================================================== pair lists (msm_pairs.cuh)
+// Round-based accumulation: per task (bucket slice, desc[t] = {first entry, padded length, slot,
+// bucket}) the number of pairs in round r is pair_count(length, r); rows r = 1 .. R-1 are scanned
+// over the tasks (blockIdx.y = r - 1) so that every round has ONE dense list.  `stride` = row pitch of
+// pairoff / chunk_sums.
+
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+pair_scan_phase1_kernel(const uint4* desc, const uint32_t* ntasks_p, uint32_t* chunk_sums, uint32_t cstride) {
+    const uint32_t n = *ntasks_p, r = blockIdx.y + 1;
+    uint32_t base = blockIdx.x * BMPC_SCAN_CHUNK + threadIdx.x * BMPC_SCAN_ITEMS;
+    uint32_t s = 0;
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++)
+        if (base + j < n) s += pair_count(__ldg(desc + base + j).y, r);
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) chunk_sums[(size_t)blockIdx.y * cstride + blockIdx.x] = total;
+}
+// one block per row: exclusive scan of the row's chunk sums in place; row total -> totals[r]
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+pair_scan_phase2_kernel(uint32_t* chunk_sums, uint32_t cstride, uint32_t nchunks, uint32_t* totals) {
+    uint32_t* row = chunk_sums + (size_t)blockIdx.x * cstride;
+    uint32_t carry = 0;
+    for (uint32_t start = 0; start < nchunks; start += BMPC_SCAN_THREADS) {
+        uint32_t idx = start + threadIdx.x;
+        uint32_t v = idx < nchunks ? row[idx] : 0u;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (idx < nchunks) row[idx] = ex + carry;
+        carry += total;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x + 1] = carry;
+}
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+pair_scan_phase3_kernel(const uint4* desc, const uint32_t* ntasks_p, const uint32_t* chunk_sums, uint32_t cstride,
+                        uint32_t* pairoff, uint32_t stride) {
+    const uint32_t n = *ntasks_p, r = blockIdx.y + 1;
+    uint32_t base = blockIdx.x * BMPC_SCAN_CHUNK + threadIdx.x * BMPC_SCAN_ITEMS;
+    uint32_t v[BMPC_SCAN_ITEMS];
+    uint32_t s = 0;
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++) {
+        v[j] = (base + j < n) ? pair_count(__ldg(desc + base + j).y, r) : 0u;
+        s += v[j];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total) + chunk_sums[(size_t)blockIdx.y * cstride + blockIdx.x];
+    for (int j = 0; j < BMPC_SCAN_ITEMS; j++) {
+        if (base + j < n) pairoff[(size_t)blockIdx.y * stride + base + j] = ex;
+        ex += v[j];
+    }
+}
+
+struct PairLayout {                       // by value into pair_build_kernel
+    uint32_t R;
+    uint32_t out_base[BMPC_PAIR_MAX_ROUNDS + 1];   // pool index of round r's first result
+    uint32_t list_off[BMPC_PAIR_MAX_ROUNDS + 1];   // first entry of round r's list in `lists` (r >= 1)
+};
+// one thread per task: the lists of rounds 1 .. R-1 and the pool index of the task's sum
+__global__ void __launch_bounds__(128)
+pair_build_kernel(const uint4* desc, const uint32_t* ntasks_p, PairLayout lay, const uint32_t* pairoff,
+                  uint32_t stride, uint2* lists, uint32_t* fin) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *ntasks_p) return;
+    const uint4 d = __ldg(desc + t);
+    uint32_t po[BMPC_PAIR_MAX_ROUNDS + 1];
+    PairIdx* lp[BMPC_PAIR_MAX_ROUNDS + 1];
+    po[0] = 0;
+    lp[0] = nullptr;
+    for (uint32_t r = 1; r < lay.R; r++) {
+        po[r] = pairoff[(size_t)(r - 1) * stride + t];
+        lp[r] = reinterpret_cast<PairIdx*>(lists + lay.list_off[r]);
+    }
+    fin[t] = pair_build_task(d.x, d.y, lay.R, po, lay.out_base, lp);
 }
 
 }  // namespace bmpc

@@ -58,7 +58,7 @@ static int get_table(bmpc_ctx* ctx, DomainTables* dt, uint32_t logm, TableKind k
                (const Fr*)nullptr, (uint64_t)1 << t.lo_bits, t.hi_n, 0, t.hi);
         // 2-level tables cost one extra product per lookup; up to 2^24 the full table is expanded
         // once (32 B per coefficient in HBM, read once per pass that uses it)
-        if (t.hi_n > 1 && logm <= DIRECT_TABLE_MAX_LOG && !(getenv("BMPC_NTT_NO_DIRECT") && atoi(getenv("BMPC_NTT_NO_DIRECT")))) {
+        if (t.hi_n > 1 && logm <= DIRECT_TABLE_MAX_LOG && !ctx->tune.ntt_no_direct) {
             uint32_t cnt = 1u << logm;
             CK(cudaMalloc(&t.direct, (size_t)cnt * sizeof(Fr)));
             PowTable two{t.hi, t.lo, t.lo_bits, t.hi_n, nullptr};

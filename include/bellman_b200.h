@@ -74,6 +74,9 @@ void bmpc_ctx_destroy(bmpc_ctx* ctx);
 const char* bmpc_last_error(const bmpc_ctx* ctx);
 /* tuning knobs (0 = automatic): MSM window bits, NTT max radix log2 */
 int  bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg);
+/* BMPC_* environment knobs (kernel selection for tests and tuning sweeps) are parsed once when the
+ * context is created; this re-reads them */
+int  bmpc_ctx_reload_env(bmpc_ctx* ctx);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx);
 
@@ -150,9 +153,10 @@ size_t bmpc_partial_bytes(int group);
  * window bits c, number of windows W (point additions per dense point), bucket sets H */
 int  bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t* window_bits,
                        uint32_t* windows, uint32_t* bucket_sets);
-/* which bucket-accumulation kernel that multiexp runs: info[0] = 1 batched-affine tree
- * (msm_affine.cuh) | 0 XYZZ chain; info[1] = slices per job, info[2] = additions per inversion per
- * thread, info[3] = thread blocks, info[4] = threads per block, info[5] = max points per slice */
+/* which bucket-accumulation kernel that multiexp runs: info[0] = 2 rounds of pair additions
+ * (msm_pairs.cuh) | 1 batched-affine tree (msm_affine.cuh) | 0 XYZZ chain; info[1] = slices per job
+ * (pair rounds: number of rounds), info[2] = additions per inversion per thread, info[3] = thread
+ * blocks, info[4] = threads per block, info[5] = max points per slice */
 int  bmpc_msm_accumulate_info(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t info[8]);
 
 /* ---- EvaluationDomain  (src/domain.rs:21-189) ------------------------------------------ */

@@ -3,6 +3,7 @@
 // Test infrastructure only.
 #include "../../bellman_mpc_b200/csrc/curve.cuh"
 #include "../../bellman_mpc_b200/csrc/msm_affine.cuh"
+#include "../../bellman_mpc_b200/csrc/msm_pairs.cuh"
 #include <vector>
 #include <string.h>
 using namespace bmpc;
@@ -39,7 +40,94 @@ static void affine_job_host(const uint32_t* bases_w, const uint32_t* sorted, con
     }
 }
 
+// The round-based pair accumulation (msm_pairs.cuh) on the host: the same list rule
+// (pair_build_task) and the same forward / backward steps the kernel runs, chunks of `chunk` pairs
+// sharing one inversion.  sorted: the padded entry array (every task an even number of entries,
+// pad = BMPC_PAIR_PAD); tasks: ntasks x {first entry, padded length}.  out_pairs / out_chain: per task
+// the affine sum by rounds and by the XYZZ chain.  Returns the number of additions listed.
+template <class F>
+static uint64_t pairs_host(const uint32_t* bases_w, const uint32_t* sorted, uint32_t nsorted, const uint32_t* tasks,
+                           uint32_t ntasks, uint32_t R, uint32_t chunk, uint32_t* out_pairs, uint32_t* out_chain) {
+    const Affine<F>* bases = reinterpret_cast<const Affine<F>*>(bases_w);
+    // per-round scans over the tasks
+    std::vector<std::vector<uint32_t>> pairoff(R, std::vector<uint32_t>(ntasks, 0));
+    std::vector<uint32_t> totals(R + 1, 0), out_base(R + 1, 0);
+    totals[0] = nsorted / 2;
+    for (uint32_t r = 1; r < R; r++) {
+        uint32_t acc = 0;
+        for (uint32_t t = 0; t < ntasks; t++) { pairoff[r][t] = acc; acc += pair_count(tasks[2 * t + 1], r); }
+        totals[r] = acc;
+    }
+    for (uint32_t r = 0; r < R; r++) out_base[r + 1] = out_base[r] + totals[r] + 3;   // slack like the host bounds
+    std::vector<std::vector<PairIdx>> lists(R);
+    for (uint32_t r = 1; r < R; r++) lists[r].resize(totals[r] + 1);
+    std::vector<uint32_t> fin(ntasks);
+    for (uint32_t t = 0; t < ntasks; t++) {
+        uint32_t po[BMPC_PAIR_MAX_ROUNDS + 1];
+        PairIdx* lp[BMPC_PAIR_MAX_ROUNDS + 1];
+        for (uint32_t r = 0; r < R; r++) { po[r] = r ? pairoff[r][t] : 0; lp[r] = r ? lists[r].data() : nullptr; }
+        fin[t] = pair_build_task(tasks[2 * t], tasks[2 * t + 1], R, po, out_base.data(), lp);
+    }
+    std::vector<Affine<F>> pool(out_base[R] + 1, Affine<F>::identity());
+    uint64_t adds = 0;
+    for (uint32_t r = 0; r < R; r++) {
+        const uint32_t P = totals[r];
+        for (uint32_t c0 = 0; c0 < P; c0 += chunk) {
+            const uint32_t kt = P - c0 < chunk ? P - c0 : chunk;
+            std::vector<F> pre(kt);
+            std::vector<Affine<F>> Ps(kt), Qs(kt);
+            F acc = F::one();
+            for (uint32_t j = 0; j < kt; j++) {
+                const uint32_t k = c0 + j;
+                bool single = false;
+                if (r == 0) {
+                    uint32_t ea = sorted[2 * k], eb = sorted[2 * k + 1];
+                    Ps[j] = bases[ea & 0x7fffffffu];
+                    if (ea >> 31) Ps[j].y = Ps[j].y.neg();
+                    single = eb == BMPC_PAIR_PAD;
+                    if (single) Qs[j] = Affine<F>::identity();
+                    else { Qs[j] = bases[eb & 0x7fffffffu]; if (eb >> 31) Qs[j].y = Qs[j].y.neg(); }
+                } else {
+                    Ps[j] = pool[lists[r][k].a];
+                    Qs[j] = pool[lists[r][k].b];
+                }
+                F d;
+                int q = pair_fwd_quick<F>(Ps[j].x, single ? Ps[j].x : Qs[j].x, single, d);
+                bool use = q == 0;
+                if (q == 2) use = aff_classify<F>(Ps[j], Qs[j], d) != 2;
+                pre[j] = acc;
+                if (use) { acc = acc * d; adds++; }
+            }
+            F inv = acc.inv();
+            for (uint32_t j = kt; j-- > 0;) pool[out_base[r] + c0 + j] = pair_bwd_add<F>(Ps[j], Qs[j], pre[j], inv);
+        }
+    }
+    for (uint32_t t = 0; t < ntasks; t++) {
+        Affine<F> v = fin[t] == BMPC_PAIR_NONE ? Affine<F>::identity() : pool[fin[t]];
+        memcpy(out_pairs + (size_t)t * sizeof(Affine<F>) / 4, &v, sizeof(Affine<F>));
+        XYZZ<F> a = XYZZ<F>::identity();
+        for (uint32_t j = 0; j < tasks[2 * t + 1]; j++) {
+            uint32_t e = sorted[tasks[2 * t] + j];
+            if (e == BMPC_PAIR_PAD) continue;
+            Affine<F> p = bases[e & 0x7fffffffu];
+            if (e >> 31) p.y = p.y.neg();
+            a.add_affine(p);
+        }
+        Affine<F> cch = a.to_affine();
+        memcpy(out_chain + (size_t)t * sizeof(Affine<F>) / 4, &cch, sizeof(Affine<F>));
+    }
+    return adds;
+}
+
 extern "C" {
+uint64_t hc_pairs_g1(const uint32_t* bases, const uint32_t* sorted, uint32_t nsorted, const uint32_t* tasks,
+                     uint32_t ntasks, uint32_t R, uint32_t chunk, uint32_t* out_pairs, uint32_t* out_chain) {
+    return pairs_host<Fp>(bases, sorted, nsorted, tasks, ntasks, R, chunk, out_pairs, out_chain);
+}
+uint64_t hc_pairs_g2(const uint32_t* bases, const uint32_t* sorted, uint32_t nsorted, const uint32_t* tasks,
+                     uint32_t ntasks, uint32_t R, uint32_t chunk, uint32_t* out_pairs, uint32_t* out_chain) {
+    return pairs_host<Fp2>(bases, sorted, nsorted, tasks, ntasks, R, chunk, out_pairs, out_chain);
+}
 uint32_t hc_affine_g() { return BMPC_AFF_G; }
 void hc_affine_job_g1(const uint32_t* bases, const uint32_t* sorted, const uint32_t* tasks, uint32_t L,
                       uint32_t* out_tree, uint32_t* out_chain) {

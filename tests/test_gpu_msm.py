@@ -15,14 +15,19 @@ from util import Q, decode, expected_from_dlogs, known_dlog_bases, rand_scalars
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["xyzz", "affine"])
-def accumulate_kernel(request, monkeypatch):
-    """Every case runs through both bucket-accumulation kernels: the XYZZ chain and the
-    batched-affine tree (msm_affine.cuh; forced here, with 3 slices per job, because the automatic
-    choice only takes it for MSMs that fill the GPU)."""
+@pytest.fixture(autouse=True, params=["xyzz", "affine", "pairs"])
+def accumulate_kernel(request, monkeypatch, worker):
+    """Every case runs through all three bucket-accumulation kernels: the XYZZ chain, the
+    batched-affine tree (msm_affine.cuh; forced here, with 3 slices per job) and the rounds of pair
+    additions (msm_pairs.cuh; forced: the automatic choice only takes them for multiexps that fill
+    the GPU)."""
+    monkeypatch.setenv("BMPC_ACC_PAIRS", "1" if request.param == "pairs" else "0")
     monkeypatch.setenv("BMPC_ACC_AFFINE", "1" if request.param == "affine" else "0")
     monkeypatch.setenv("BMPC_AFF_FORCE_G", "3")
+    worker.reload_env()
     yield request.param
+    monkeypatch.undo()
+    worker.reload_env()
 
 
 def _oracle_points(group, ks):

@@ -138,3 +138,78 @@ def test_batched_affine_job(lib, which):
             p = pts[e & 0x7FFFFFFF]
             expect = G.add(expect, G.neg(p) if e >> 31 else p)
         assert dec(tree[g * words:(g + 1) * words]) == expect, (which, g)
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_pair_rounds(lib, which):
+    """msm_pairs.cuh on the host: the per-slice list rule (pair_build_task: round-0 pairs straight from
+    the even-padded entry array, explicit lists with a CARRIED odd element afterwards) and the forward
+    / backward steps of the round kernel == the XYZZ chain == the oracle's sum, for slices of length
+    1/2/3/odd/even/one full 2^R slice, with duplicates (tangent), opposite points, identity bases;
+    and a slice of k distinct points costs exactly k - 1 additions."""
+    P, Rm = fields.Fp.p, fields.Fp.R
+    Ri = pow(Rm, -1, P)
+    fl = lambda x: [((x * Rm % P) >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+    fv = lambda l: _v(l) * Ri % P
+    rng = random.Random(9)
+    if which == "g1":
+        G, fn, words = curves.G1, lib.hc_pairs_g1, 24
+        enc = lambda p: [0] * 24 if p is None else fl(p[0]) + fl(p[1])
+        dec = lambda a: None if not any(a) else (fv(a[:12]), fv(a[12:]))
+    else:
+        G, fn, words = curves.G2, lib.hc_pairs_g2, 48
+        enc = lambda p: [0] * 48 if p is None else fl(p[0][0]) + fl(p[0][1]) + fl(p[1][0]) + fl(p[1][1])
+        dec = lambda a: None if not any(a) else ((fv(a[:12]), fv(a[12:24])), (fv(a[24:36]), fv(a[36:])))
+    fn.restype = ctypes.c_uint64
+    nb = 40
+    pts = [G.mul(G.gen, rng.randrange(1, fields.Fr.p)) for _ in range(nb - 1)] + [None]
+    bases = (ctypes.c_uint32 * (words * nb))(*sum((enc(p) for p in pts), []))
+    R = 6                                            # slices of at most 64 entries
+    PAD = 0xFFFFFFFF
+    for special in (False, True):
+        lens = [1, 2, 3, 4, 5, 7, 8, 9, 17, 31, 33, 63, 64, 64] + [rng.randrange(1, 65) for _ in range(12)]
+        entries, tasks, real = [], [], []
+        for ln in lens:
+            start = len(entries)
+            mine = []
+            for j in range(ln):
+                r = rng.random()
+                if special and r < 0.15 and j > 0:
+                    e = mine[-1] ^ 0x80000000                 # the negative of the previous point
+                elif special and r < 0.3 and j > 0:
+                    e = mine[-1]                              # the same point again (tangent)
+                elif special:
+                    e = rng.randrange(nb) | (rng.randrange(2) << 31)
+                else:
+                    e = (start + 7 * j) % (nb - 1) if False else rng.randrange(nb - 1) | (rng.randrange(2) << 31)
+                mine.append(e)
+            if not special:                                   # distinct points in every slice: no special case
+                idx = rng.sample(range(nb - 1), min(ln, nb - 1))
+                mine = [(idx[j % len(idx)] if ln <= nb - 1 else rng.randrange(nb - 1)) | (rng.randrange(2) << 31)
+                        for j in range(ln)]
+                if ln > nb - 1:
+                    mine = None
+            if mine is None:
+                continue
+            entries += mine + ([PAD] if ln % 2 else [])
+            tasks += [start, ln + ln % 2]
+            real.append(mine)
+        nt = len(real)
+        srt = (ctypes.c_uint32 * len(entries))(*entries)
+        tk = (ctypes.c_uint32 * (2 * nt))(*tasks)
+        for chunk in (1, 5, 1000):
+            out_pairs = (ctypes.c_uint32 * (words * nt))()
+            out_chain = (ctypes.c_uint32 * (words * nt))()
+            adds = fn(bases, srt, len(entries), tk, nt, R, chunk, out_pairs, out_chain)
+            assert list(out_pairs) == list(out_chain), (which, special, chunk)
+            if not special:
+                assert adds == sum(len(m) - 1 for m in real)
+            else:
+                assert adds <= sum(len(m) - 1 for m in real)
+        got = list(out_pairs)
+        for t, mine in enumerate(real):
+            expect = None
+            for e in mine:
+                p = pts[e & 0x7FFFFFFF]
+                expect = G.add(expect, G.neg(p) if e >> 31 else p)
+            assert dec(got[t * words:(t + 1) * words]) == expect, (which, special, t)
