@@ -47,6 +47,36 @@ def fp2_inv(a):
     return (a[0] * n % P, (-a[1]) * n % P)
 
 
+def fp_sqrt(a):
+    """p = 3 mod 4: a^((p+1)/4), None when a is not a square"""
+    r = pow(a, (P + 1) // 4, P)
+    return r if r * r % P == a % P else None
+
+
+def fp2_sqrt(a):
+    """Square root in Fp[u]/(u^2+1) for p = 3 mod 4 (Adj & Rodriguez-Henriquez, alg. 9), None for a
+    non-residue."""
+    if a == (0, 0):
+        return (0, 0)
+
+    def fpow(x, e):
+        r = (1, 0)
+        while e:
+            if e & 1:
+                r = fp2_mul(r, x)
+            x = fp2_mul(x, x)
+            e >>= 1
+        return r
+    a1 = fpow(a, (P - 3) // 4)
+    alpha = fp2_mul(a1, fp2_mul(a1, a))
+    x0 = fp2_mul(a1, a)
+    if alpha == (P - 1, 0):
+        r = fp2_mul((0, 1), x0)
+    else:
+        r = fp2_mul(fpow(fp2_add((1, 0), alpha), (P - 1) // 2), x0)
+    return r if fp2_mul(r, r) == (a[0] % P, a[1] % P) else None
+
+
 def fp2_scalar(a, k):
     return (a[0] * k % P, a[1] * k % P)
 
@@ -253,6 +283,40 @@ class CurveGroup:
         return bytes(out)
 
 
+    def from_compressed(self, b):
+        """bls12_381 `from_compressed` (the GroupEncoding::from_bytes that Proof::read calls,
+        groth16/mod.rs:50-103): flag bits, canonical coordinates, on-curve by construction of y,
+        sign bit, and the prime-order subgroup check.  None = the CtOption is none."""
+        n = self.coord_bytes
+        if len(b) != n or not (b[0] & 0x80):
+            return None
+        inf, sign = bool(b[0] & 0x40), bool(b[0] & 0x20)
+        body = bytes([b[0] & 0x1F]) + bytes(b[1:])
+        if n == 96:
+            c1, c0 = int.from_bytes(body[:48], "big"), int.from_bytes(body[48:], "big")
+            if c0 >= P or c1 >= P:
+                return None
+            x = (c0, c1)
+        else:
+            x = int.from_bytes(body, "big")
+            if x >= P:
+                return None
+        if inf:
+            zero = x == ((0, 0) if n == 96 else 0)
+            return "identity" if (zero and not sign) else None
+        F = self.F
+        rhs = F.add(F.mul(F.mul(x, x), x), self.b)
+        y = fp2_sqrt(rhs) if n == 96 else fp_sqrt(rhs)
+        if y is None:
+            return None
+        if self._lex_largest(y) != sign:
+            y = F.neg(y)
+        pt = (x, y)
+        if self.mul(pt, Fr.p) is not None:
+            return None
+        return pt
+
+
 G1_GEN = (
     0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB,
     0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1,
@@ -321,4 +385,9 @@ def self_check():
     assert G1.to_compressed(G1_GEN).hex().startswith("97f1d3a73197d794")
     assert G1.from_uncompressed(G1.to_uncompressed(two)) == two
     assert G2.from_uncompressed(G2.to_uncompressed(G2_GEN)) == G2_GEN
+    for G in (G1, G2):
+        for k in (1, 2, 3, 0xDEADBEEF):
+            pt = G.mul(G.gen, k)
+            assert G.from_compressed(G.to_compressed(pt)) == pt
+        assert G.from_compressed(G.to_compressed(None)) == "identity"
     return True

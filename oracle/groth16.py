@@ -14,8 +14,8 @@ Follows /root/reference/bellman/src/groth16/:
                           assert/print and make keygen panic beyond 4-constraint toys
                           
   generator.rs:34-38      the fork's fixed toxic waste alpha=6 beta=24 gamma=6 delta=24 tau=2
-  verifier.rs:23-62       verify_proof (only usable with an engine that has a pairing:
-                          the DummyEngine here; for BLS12-381 use `expected_proof`)
+  verifier.rs:10-62       prepare_verifying_key / verify_proof (DummyEngine: Gt = Fr, additive;
+                          BLS12-381: the optimal ate pairing of oracle/pairing.py)
 
 Engines: BLS12-381 (oracle.curves.G1/G2 over oracle.fields.Fr) and the reference's
 DummyEngine (groth16/tests/dummy_engine.rs) so the golden vectors in
@@ -23,21 +23,28 @@ groth16/tests/mod.rs:334-435,574 pin this restatement.
 """
 from __future__ import annotations
 
-from . import curves, fields
+from . import curves, fields, pairing as _pairing
 from .domain import EvaluationDomain
 from .multiexp import (DensityTracker, FullDensity, SynthesisError, UnexpectedIdentity,
                        multiexp)
 
 
 class Engine:
-    def __init__(self, name, Fr, G1, G2, pairing=None):
+    """pairing::{Engine, MultiMillerLoop}: `pairing(p, q)` and `multi_miller_final(pairs)` =
+    `multi_miller_loop(pairs).final_exponentiation()`; Gt values are compared with ==."""
+
+    def __init__(self, name, Fr, G1, G2, pairing=None, multi_miller_final=None):
         self.name, self.Fr, self.G1, self.G2, self.pairing = name, Fr, G1, G2, pairing
+        self.multi_miller_final = multi_miller_final
 
 
-BLS12 = Engine("Bls12", fields.Fr, curves.G1, curves.G2)
-# dummy_engine.rs:354-364: pairing(p, q) = p * q in Fr; Gt "multiplication" = addition
+BLS12 = Engine("Bls12", fields.Fr, curves.G1, curves.G2, pairing=_pairing.pairing,
+               multi_miller_final=lambda pairs: _pairing.final_exponentiation(_pairing.multi_miller_loop(pairs)))
+# dummy_engine.rs:344-364: pairing(p, q) = p * q in Fr; Gt "multiplication" = addition, the Miller
+# loop result is the sum of the products and the final exponentiation the identity map
 DUMMY = Engine("DummyEngine", fields.DummyFr, curves.Dummy, curves.Dummy,
-               pairing=lambda p, q: p * q % 64513)
+               pairing=lambda p, q: p * q % 64513,
+               multi_miller_final=lambda pairs: sum(p * q for p, q in pairs) % 64513)
 
 ONE = ("input", 0)   # ConstraintSystem::one()  (lib.rs)
 
@@ -210,6 +217,25 @@ class Proof:
                 + engine.G1.to_compressed(self.c))
 
 
+    @staticmethod
+    def read(engine, data):
+        """mod.rs:50-103: three compressed points; "invalid G1/G2" for an undecodable one, "point at
+        infinity" for the identity, UnexpectedEof for a short buffer (ValueError carries the message)."""
+        n1, n2 = engine.G1.coord_bytes, engine.G2.coord_bytes
+        if len(data) < 2 * n1 + n2:
+            raise ValueError("UnexpectedEof")
+        pts, off = [], 0
+        for G, n, name in ((engine.G1, n1, "G1"), (engine.G2, n2, "G2"), (engine.G1, n1, "G1")):
+            pt = G.from_compressed(bytes(data[off:off + n]))
+            off += n
+            if pt is None:
+                raise ValueError("invalid " + name)
+            if pt == "identity":
+                raise ValueError("point at infinity")
+            pts.append(pt)
+        return Proof(*pts)
+
+
 def synthesize_for_proving(engine, circuit):
     """prover.rs:187-204: alloc ONE, synthesize, one `x * 0 = 0` per input."""
     prover = ProvingAssignment(engine.Fr)
@@ -279,19 +305,45 @@ def create_random_proof(engine, circuit, params):
 
 
 # -------------------------------------------------------------------------- verifier
-def verify_proof(engine, vk, proof, public_inputs):
-    """verifier.rs:23-62, for engines that carry a pairing (DummyEngine: Gt additive)."""
-    assert engine.pairing is not None
+class PreparedVerifyingKey:
+    """groth16/mod.rs:403-414"""
+
+    def __init__(self, alpha_g1_beta_g2, neg_gamma_g2, neg_delta_g2, ic):
+        self.alpha_g1_beta_g2, self.neg_gamma_g2, self.neg_delta_g2, self.ic = (
+            alpha_g1_beta_g2, neg_gamma_g2, neg_delta_g2, ic)
+
+
+def prepare_verifying_key(engine, vk):
+    """verifier.rs:10-21"""
+    G2 = engine.G2
+    return PreparedVerifyingKey(engine.pairing(vk.alpha_g1, vk.beta_g2), G2.neg(vk.gamma_g2),
+                                G2.neg(vk.delta_g2), list(vk.ic))
+
+
+class InvalidVerifyingKey(Exception):
+    """VerificationError::InvalidVerifyingKey (lib.rs)"""
+
+
+def verify_proof_prepared(engine, pvk, proof, public_inputs):
+    """verifier.rs:23-62: Err(InvalidVerifyingKey) raises, Err(InvalidProof) -> False, Ok -> True."""
     G1 = engine.G1
-    if len(public_inputs) + 1 != len(vk.ic):
-        return False
-    acc = vk.ic[0]
-    for i, b in zip(public_inputs, vk.ic[1:]):
+    if len(public_inputs) + 1 != len(pvk.ic):
+        raise InvalidVerifyingKey()
+    acc = pvk.ic[0]
+    for i, b in zip(public_inputs, pvk.ic[1:]):
         acc = G1.add(acc, G1.mul(b, i))
-    e, mod = engine.pairing, engine.Fr.p
-    lhs = e(proof.a, proof.b)
-    rhs = (e(vk.alpha_g1, vk.beta_g2) + e(acc, vk.gamma_g2) + e(proof.c, vk.delta_g2)) % mod
-    return lhs == rhs
+    # A * B + inputs * (-gamma) + C * (-delta) = alpha * beta with a single final exponentiation
+    return pvk.alpha_g1_beta_g2 == engine.multi_miller_final(
+        [(proof.a, proof.b), (acc, pvk.neg_gamma_g2), (proof.c, pvk.neg_delta_g2)])
+
+
+def verify_proof(engine, vk, proof, public_inputs):
+    """prepare_verifying_key + verify_proof as the reference's tests chain them
+    (groth16/tests/mod.rs:574-585, tests/mimc.rs); a wrong input count returns False."""
+    try:
+        return verify_proof_prepared(engine, prepare_verifying_key(engine, vk), proof, public_inputs)
+    except InvalidVerifyingKey:
+        return False
 
 
 # ------------------------------------------------------------- known-trapdoor expectation

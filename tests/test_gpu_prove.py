@@ -45,6 +45,10 @@ def test_xor_demo(worker):
         assert len(proof) == 192
         assert proof == og.create_proof_from_assignment(E, prover, params, 27134, 17146).to_bytes(E)
         assert proof == og.expected_proof(E, params, prover, 27134, 17146).to_bytes(E)
+        # the reference verifier (verifier.rs:23-62) accepts the bytes the GPU produced
+        got = og.Proof.read(E, proof)
+        assert og.verify_proof(E, params.vk, got, [int(a ^ b)])
+        assert not og.verify_proof(E, params.vk, got, [int(not (a ^ b))])
 
 
 def test_mimc(worker):
@@ -63,6 +67,44 @@ def test_mimc(worker):
     assert prover.b_aux_density.get_total_density() == 322
     proof = bm.create_random_proof(to_gpu_assignment(prover), gp)
     assert proof == og.expected_proof(E, params, prover, 27134, 17146).to_bytes(E)
+    # config #1 is "prove + verify": Proof::read, prepare_verifying_key, verify_proof (tests/mimc.rs)
+    pvk = og.prepare_verifying_key(E, params.vk)
+    got = og.Proof.read(E, proof)
+    image = og.mimc(F, xl, xr, constants)
+    assert og.verify_proof_prepared(E, pvk, got, [image])
+    assert not og.verify_proof_prepared(E, pvk, got, [(image + 1) % Q])
+
+
+def test_synthetic_2p14_proof_accepted_by_the_verifier(worker):
+    """A satisfiable random R1CS with 2^14 constraints (16 inputs, one aux variable per constraint):
+    key generation, constraint evaluation and create_proof all on the GPU; the 192 proof bytes go
+    through Proof::read and the reference's verification equation with the oracle's pairing.  Needs no
+    known-dlog expectation: acceptance is an independent statement about H, the four query
+    multiexps and the tail."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench"))
+    import r1cs_bench
+    from oracle import params_io as pio
+    E = og.BLS12
+    sysd = r1cs_bench.build(14, seed=11)
+    n, ni, na = sysd["n"], sysd["ni"], sysd["na"]
+    asg = bm.r1cs_eval(worker, sysd["A"], sysd["B"], sysd["C"], bm.fr_to_mont(sysd["w"][:ni]),
+                       bm.fr_to_mont(sysd["w"][ni:]))
+    T = [r1cs_bench.transpose(M, ni + na) for M in (sysd["A"], sysd["B"], sysd["C"])]
+    G1, G2 = curves.G1, curves.G2
+    gp = bm.generate_parameters(worker, *T, ni, na, n, G1.to_uncompressed(G1.gen), G2.to_uncompressed(G2.gen),
+                                6, 24, 6, 24, 2)
+    proof = bm.create_random_proof(asg, gp)
+    vk = pio.read_vk(pio._Reader(gp.write()))
+    assert len(vk.ic) == ni
+    pvk = og.prepare_verifying_key(E, vk)
+    got = og.Proof.read(E, proof)
+    public = sysd["w"][1:ni]
+    assert og.verify_proof_prepared(E, pvk, got, public)
+    wrong = list(public)
+    wrong[3] = (wrong[3] + 1) % Q
+    assert not og.verify_proof_prepared(E, pvk, got, wrong)
+    gp.free()
 
 
 def test_delta_identity_rejected(worker):
