@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v
 SRC       := bellman_mpc_b200/csrc
 OBJDIR    := build/obj
-UNITS     := api ntt msm_sort group_g1 group_g2 prove r1cs
+UNITS     := api multi ntt msm_sort group_g1 group_g2 prove r1cs
 OBJS      := $(UNITS:%=$(OBJDIR)/%.o)
 LIB       := bellman_mpc_b200/libbellman_b200.so
 HDRS      := $(wildcard $(SRC)/*.cuh) $(SRC)/internal.h include/bellman_b200.h

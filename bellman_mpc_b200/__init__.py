@@ -51,9 +51,15 @@ class InvalidData(IoError):
     """io::ErrorKind::InvalidData from Parameters::read ("invalid G1", "point at infinity")"""
 
 
-def _raise(status, ctx=None):
+def _raise(status, ctx=None, msg_override=None):
     if status == _lib.OK:
         return
+    if msg_override is not None and status in (_lib.ERR_CUDA, _lib.ERR_INVALID, _lib.ERR_INVALID_DATA):
+        if status == _lib.ERR_CUDA:
+            raise IoError(f"CUDA error: {msg_override}")
+        if status == _lib.ERR_INVALID_DATA:
+            raise InvalidData(msg_override)
+        raise ValueError(f"invalid argument ({msg_override})")
     if status == _lib.ERR_UNEXPECTED_IDENTITY:
         raise UnexpectedIdentity()
     if status == _lib.ERR_UNEXPECTED_EOF:
@@ -139,19 +145,129 @@ class Worker:
 
 
 class Waiter:
-    """multicore.rs:93-118: `wait()` returns the Result (raises the SynthesisError)."""
+    """multicore.rs:93-118: `wait()` returns the Result (raises the SynthesisError).  A waiter made by
+    `multiexp` holds a bmpc_waiter: the multiexp is in flight on a lane of the context and wait()
+    blocks for it (bmpc_waiter_wait)."""
 
-    def __init__(self, value=None, error=None):
-        self._value, self._error = value, error
+    def __init__(self, value=None, error=None, pending=None):
+        self._value, self._error, self._pending = value, error, pending
 
     @staticmethod
     def done(value):
         return Waiter(value=value)
 
     def wait(self):
+        if self._pending is not None:
+            pool, handle, out, keep = self._pending
+            self._pending = None
+            st = pool._lib.bmpc_waiter_wait(handle, _ptr(out))
+            del keep                                   # scalars / density words had to outlive the call
+            try:
+                _raise(st, pool.ctx)
+                self._value = out.tobytes()
+            except SynthesisError as e:
+                self._error = e
         if self._error is not None:
             raise self._error
         return self._value
+
+    def __del__(self):
+        # a waiter that is dropped still has to give its lane back
+        try:
+            if self._pending is not None:
+                self.wait()
+        except Exception:
+            pass
+
+
+class MultiWorker:
+    """All GPUs of a node behind one Worker (SURVEY 8b `bmpc_ctx_create(devices, n)`): `multiexp` and
+    `create_proof` stay single calls; the library shards them over the devices (csrc/multi.cu)."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        st = self._lib.bmpc_multi_create(devs, len(devices), C.byref(h))
+        if st != _lib.OK:
+            raise IoError(f"bmpc_multi_create({list(devices)}) failed with status {st}: "
+                          "no usable CUDA device (there is no CPU fallback)")
+        self.handle = h
+        self.devices = list(devices)
+
+    def __len__(self):
+        return int(self._lib.bmpc_multi_size(self.handle))
+
+    def last_error(self):
+        return self._lib.bmpc_multi_last_error(self.handle).decode()
+
+    def rank_ctx(self, rank):
+        return C.c_void_p(self._lib.bmpc_multi_ctx(self.handle, rank))
+
+    def close(self):
+        if self.handle:
+            self._lib.bmpc_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBases:
+    """A base vector split evenly over the devices of a MultiWorker (bmpc_multi_bases)."""
+
+    def __init__(self, worker, group, handle):
+        self.worker, self.group, self.handle = worker, group, handle
+        self._lib = worker._lib
+
+    @staticmethod
+    def from_uncompressed(worker, group, data, n=None):
+        pb = 96 if group == G1 else 192
+        buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        if n is None:
+            n = buf.size // pb
+        h = C.c_void_p()
+        _raise(worker._lib.bmpc_multi_bases_register(worker.handle, group, _ptr(buf), n, pb, FORM_UNCOMPRESSED_BE,
+                                                     C.byref(h)), None, worker.last_error())
+        return MultiBases(worker, group, h)
+
+    def precompute(self, window_bits=0):
+        _raise(self._lib.bmpc_multi_bases_precompute(self.worker.handle, self.handle, window_bits), None,
+               self.worker.last_error())
+        return self
+
+    def __len__(self):
+        return int(self._lib.bmpc_multi_bases_len(self.handle))
+
+    def free(self):
+        if self.handle:
+            self._lib.bmpc_multi_bases_free(self.worker.handle, self.handle)
+            self.handle = None
+
+
+class MultiParameters:
+    """groth16/mod.rs:224-247 with every query vector split over the devices of a MultiWorker."""
+
+    def __init__(self, worker, h, l, a, b_g1, b_g2, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2):
+        self.worker = worker
+        self.h, self.l, self.a, self.b_g1, self.b_g2 = h, l, a, b_g1, b_g2
+        self.alpha_g1, self.beta_g1, self.beta_g2 = bytes(alpha_g1), bytes(beta_g1), bytes(beta_g2)
+        self.delta_g1, self.delta_g2 = bytes(delta_g1), bytes(delta_g2)
+
+    def _struct(self):
+        p = _lib.MultiParams()
+        p.h, p.l, p.a, p.b_g1, p.b_g2 = (self.h.handle, self.l.handle, self.a.handle, self.b_g1.handle,
+                                         self.b_g2.handle)
+        for name in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2"):
+            C.memmove(getattr(p, name), getattr(self, name), len(getattr(self, name)))
+        return p
+
+    def free(self):
+        for b in (self.h, self.l, self.a, self.b_g1, self.b_g2):
+            b.free()
 
 
 # ----------------------------------------------------------------------------- bases
@@ -327,13 +443,22 @@ def multiexp(pool, bases, density_map, exponents):
     words = density_map.words()
     pb = 96 if src.group == G1 else 192
     out = np.zeros(pb, dtype=np.uint8)
-    st = pool._lib.bmpc_multiexp(pool.ctx, src.handle, start, _ptr(exps), n, _ptr(words),
-                                 n if words is not None else 0, _ptr(out))
+    if isinstance(pool, MultiWorker):
+        st = pool._lib.bmpc_multi_multiexp(pool.handle, src.handle, start, _ptr(exps), n, _ptr(words),
+                                           n if words is not None else 0, _ptr(out))
+        try:
+            _raise(st, None, pool.last_error())
+        except SynthesisError as e:
+            return Waiter(error=e)
+        return Waiter.done(out.tobytes())
+    h = C.c_void_p()
+    st = pool._lib.bmpc_multiexp_async(pool.ctx, src.handle, start, _ptr(exps), n, _ptr(words),
+                                       n if words is not None else 0, C.byref(h))
     try:
         _raise(st, pool.ctx)
     except SynthesisError as e:
         return Waiter(error=e)
-    return Waiter.done(out.tobytes())
+    return Waiter(pending=(pool, h, out, (exps, words)))
 
 
 # ------------------------------------------------------------------ EvaluationDomain
@@ -504,7 +629,11 @@ def create_proof(assignment, params, r_mont, s_mont):
     r = np.ascontiguousarray(r_mont, dtype=np.uint64).reshape(4)
     sv = np.ascontiguousarray(s_mont, dtype=np.uint64).reshape(4)
     out = np.zeros(192, dtype=np.uint8)
-    _raise(w._lib.bmpc_create_proof(w.ctx, C.byref(p), C.byref(s), _ptr(r), _ptr(sv), _ptr(out)), w.ctx)
+    if isinstance(w, MultiWorker):
+        _raise(w._lib.bmpc_multi_create_proof(w.handle, C.byref(p), C.byref(s), _ptr(r), _ptr(sv), _ptr(out)),
+               None, w.last_error())
+    else:
+        _raise(w._lib.bmpc_create_proof(w.ctx, C.byref(p), C.byref(s), _ptr(r), _ptr(sv), _ptr(out)), w.ctx)
     return out.tobytes()
 
 

@@ -36,6 +36,10 @@ EXPORTS = [
     "bmpc_list_mul_matrix",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
     "bmpc_r1cs_eval", "bmpc_generate_parameters",
+    "bmpc_multiexp_async", "bmpc_waiter_wait",
+    "bmpc_multi_create", "bmpc_multi_destroy", "bmpc_multi_size", "bmpc_multi_ctx", "bmpc_multi_last_error",
+    "bmpc_multi_bases_register", "bmpc_multi_bases_precompute", "bmpc_multi_bases_len", "bmpc_multi_bases_part",
+    "bmpc_multi_bases_free", "bmpc_multi_multiexp", "bmpc_multi_create_proof",
 ]
 
 
@@ -54,6 +58,11 @@ class Assignment(C.Structure):
                 ("aux_assignment", C.c_void_p), ("num_aux", C.c_size_t),
                 ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p),
                 ("b_aux_density", C.c_void_p)]
+
+
+class MultiParams(C.Structure):
+    """bmpc_multi_params"""
+    _fields_ = Params._fields_
 
 
 PROOF_PARTIAL_BYTES = 1920      # BMPC_PROOF_PARTIAL_BYTES: 6 G1 XYZZ (192 B) + 2 G2 XYZZ (384 B)
@@ -151,6 +160,20 @@ def load():
         "bmpc_r1cs_eval": (i32, [vp, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Csr), sz, sz, vp, vp, vp, vp, vp, vp, vp, vp]),
         "bmpc_generate_parameters": (i32, [vp, C.POINTER(Csr), C.POINTER(Csr), C.POINTER(Csr), sz, sz, sz, vp, vp,
                                            vp, vp, vp, vp, vp, C.POINTER(ParametersFile)]),
+        "bmpc_multiexp_async": (i32, [vp, vp, sz, vp, sz, vp, sz, C.POINTER(vp)]),
+        "bmpc_waiter_wait": (i32, [vp, vp]),
+        "bmpc_multi_create": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]),
+        "bmpc_multi_destroy": (None, [vp]),
+        "bmpc_multi_size": (i32, [vp]),
+        "bmpc_multi_ctx": (vp, [vp, i32]),
+        "bmpc_multi_last_error": (C.c_char_p, [vp]),
+        "bmpc_multi_bases_register": (i32, [vp, i32, vp, sz, sz, i32, C.POINTER(vp)]),
+        "bmpc_multi_bases_precompute": (i32, [vp, vp, i32]),
+        "bmpc_multi_bases_len": (sz, [vp]),
+        "bmpc_multi_bases_part": (vp, [vp, i32, C.POINTER(sz)]),
+        "bmpc_multi_bases_free": (None, [vp, vp]),
+        "bmpc_multi_multiexp": (i32, [vp, vp, sz, vp, sz, vp, sz, vp]),
+        "bmpc_multi_create_proof": (i32, [vp, C.POINTER(MultiParams), C.POINTER(Assignment), vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -12,7 +12,7 @@
 
 using namespace bmpc;
 
-namespace {
+namespace bmpc {
 
 int flags_to_status(uint32_t flags) {
     // SURVEY 8a'/5: EOF fails every window; an identity only the windows that consume it.
@@ -27,22 +27,12 @@ void write_identity(int group, uint8_t* out) {
     out[0] = 0x40;
 }
 
-// A multiexp in flight: everything is enqueued on `st`, the flags word (and the result bytes)
-// land in the pinned staging area at `h`; multiexp_collect turns them into the reference's status
-// once the stream has been synchronised.  create_proof enqueues all eight before waiting once.
-struct MsmPending {
-    cudaStream_t st = nullptr;     // nullptr: nothing was launched (n == 0), status OK
-    const uint8_t* h = nullptr;
-    size_t out_bytes = 0;
-    uint8_t* out = nullptr;
-};
-
 // n_ref: the length of the WHOLE exponent vector when this call is one shard of it (the reference
 // derives its window size -- and with it which error wins -- from that length, multiexp.rs:267-271);
 // 0 = this call is the whole multiexp.
 int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* d_scalars,
                      size_t n, const uint64_t* d_density, size_t density_len, uint8_t* out, void* d_partial,
-                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend, size_t n_ref = 0) {
+                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend, size_t n_ref) {
     *pend = MsmPending();
     if (!bases || (!out && !d_partial)) return BMPC_ERR_INVALID;
     if (d_density && density_len != n) return BMPC_ERR_LENGTH_MISMATCH;  // multiexp.rs:273-278
@@ -88,7 +78,7 @@ int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
 }
 
 // after the stream was synchronised
-int multiexp_collect(const MsmPending& pend, uint32_t* flags_out = nullptr) {
+int multiexp_collect(const MsmPending& pend, uint32_t* flags_out) {
     if (flags_out) *flags_out = 0;
     if (!pend.st) return BMPC_OK;
     uint32_t flags = *reinterpret_cast<const uint32_t*>(pend.h);
@@ -101,7 +91,7 @@ int multiexp_collect(const MsmPending& pend, uint32_t* flags_out = nullptr) {
 int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
                         const uint64_t* d_scalars, size_t n, const uint64_t* d_density,
                         size_t density_len, uint8_t* out, void* d_partial, cudaStream_t st,
-                        size_t n_ref = 0, uint32_t* flags_out = nullptr) {
+                        size_t n_ref, uint32_t* flags_out) {
     MsmPending pend;
     int rc = multiexp_enqueue(ctx, bases, base_offset, d_scalars, n, d_density, density_len, out, d_partial, st,
                               ctx->h_stage, &pend, n_ref);
@@ -109,6 +99,10 @@ int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offs
     if (pend.st) CK(cudaStreamSynchronize(st));
     return multiexp_collect(pend, flags_out);
 }
+
+}  // namespace bmpc
+
+namespace {
 
 // a bmpc_bases under construction: device memory and the handle are released unless handed out
 struct BasesGuard {
@@ -137,7 +131,7 @@ int register_points(bmpc_ctx* ctx, bmpc_bases* b, cudaStream_t st) {
 
 void bmpc_tuning::load() {
     auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-    acc_pairs = geti("BMPC_ACC_PAIRS", -1);
+    acc_pairs = geti("BMPC_ACC_PAIRS", 0);
     const char* me = getenv("BMPC_PAIR_MIN_ENTRIES");
     pair_min_entries = me ? (size_t)atoll(me) : ((size_t)1 << 22);
     pair_k = geti("BMPC_PAIR_K", 0);
@@ -183,6 +177,8 @@ int bmpc_ctx_create(int device, bmpc_ctx** out) {
 
 void bmpc_ctx_destroy(bmpc_ctx* ctx) {
     if (!ctx) return;
+    for (bmpc_ctx* lane : ctx->lanes) bmpc_ctx_destroy(lane);
+    ctx->lanes.clear();
     DeviceGuard dg(ctx->device);
     cudaDeviceSynchronize();
     ntt_free_tables(ctx);
@@ -210,6 +206,7 @@ int bmpc_ctx_set_tuning(bmpc_ctx* ctx, int msm_window_bits, int ntt_max_deg) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->tune_c = msm_window_bits;
     ctx->tune_maxdeg = ntt_max_deg;
+    for (bmpc_ctx* lane : ctx->lanes) lane->tune_c = msm_window_bits;
     return BMPC_OK;
 }
 
@@ -217,10 +214,16 @@ int bmpc_ctx_reload_env(bmpc_ctx* ctx) {
     if (!ctx) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->tune.load();
+    for (bmpc_ctx* lane : ctx->lanes) lane->tune = ctx->tune;
     return BMPC_OK;
 }
 
-uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t bmpc_ctx_launch_count(const bmpc_ctx* ctx) {
+    if (!ctx) return 0;
+    uint64_t total = ctx->launches;
+    for (const bmpc_ctx* lane : ctx->lanes) total += lane->launches;
+    return total;
+}
 
 int bmpc_ctx_profile(bmpc_ctx* ctx, int enable) {
     if (!ctx) return BMPC_ERR_INVALID;
@@ -757,20 +760,21 @@ int bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* st
 
 // ----------------------------------------------------------------------- create_proof
 }  // extern "C"
-namespace {
-// Shared body of bmpc_create_proof (shard == NULL: the eight multiexps, then the tail, 192-byte
-// proof) and bmpc_create_proof_partials (one rank's share of the multiexps: `S` is the rank's
-// SLICE of the assignment, shard->base_offset[j] the first base each multiexp consumes inside the
-// rank's slice of the query vector, [h_lo, h_hi) its share of the H coefficients; the XYZZ partial
-// sums go to partials_out, the per-multiexp raw flag words to flags_out, no tail).
+namespace bmpc {
+// Shared body of bmpc_create_proof (slices == NULL, partials_out == NULL: the eight multiexps over
+// their whole exponent vectors, then the tail, 192-byte proof) and of one device's / rank's share of
+// a sharded proof (partials_out != NULL: `S` is the assignment the positions of `slices` index into,
+// `P` the device's slices of the query vectors; the XYZZ partial sums go to partials_out, the
+// per-multiexp raw flag words to flags_out, no tail).
 int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
-                        const uint64_t s[4], const bmpc_proof_shard* shard, uint8_t* proof_out,
+                        const uint64_t s[4], const ProofSlices* slices, uint8_t* proof_out,
                         uint8_t* partials_out, uint32_t* flags_out) {
     if (!P->h || !P->l || !P->a || !P->b_g1 || !P->b_g2) return BMPC_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->own_stream;
     StreamScope ss(ctx, st);
+    const bool partial_mode = partials_out != nullptr;
     const size_t nc = S->num_constraints, ni = S->num_inputs, na = S->num_aux;
     size_t m = 1;
     uint32_t exp = 0;
@@ -779,15 +783,64 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         exp++;
         if (exp >= 32) return BMPC_ERR_DEGREE_TOO_LARGE;  // from_coeffs, prover.rs:211
     }
+    // the eight multiexps (prover.rs:233,252-307) over their whole exponent vectors unless sliced
+    ProofSlices whole;
+    if (!slices) {
+        size_t b_in_total = 0;
+        for (size_t i = 0; i < ni; i++) b_in_total += (S->b_input_density[i / 64] >> (i % 64)) & 1;
+        const size_t his[8] = {ni, na, ni, na, ni, na, m - 1, na};
+        const size_t offs[8] = {0, ni, 0, b_in_total, 0, b_in_total, 0, 0};
+        const uint64_t* ds[8] = {nullptr, S->a_aux_density, S->b_input_density, S->b_aux_density,
+                                 S->b_input_density, S->b_aux_density, nullptr, nullptr};
+        for (int j = 0; j < 8; j++) {
+            whole.lo[j] = 0; whole.hi[j] = his[j]; whole.base_offset[j] = offs[j]; whole.n_total[j] = 0;
+            whole.dens[j] = ds[j];
+        }
+        slices = &whole;
+    }
+    const ProofSlices& SL = *slices;
+    {
+        const size_t lim[8] = {ni, na, ni, na, ni, na, m - 1, na};
+        for (int j = 0; j < 8; j++)
+            if (SL.lo[j] > SL.hi[j] || SL.hi[j] > lim[j]) return BMPC_ERR_INVALID;
+    }
+    // the ranges of the input / aux assignment this call touches
+    auto span = [&](const int* js, int cnt, size_t* lo, size_t* hi) {
+        *lo = *hi = 0;
+        bool any = false;
+        for (int k = 0; k < cnt; k++) {
+            const int j = js[k];
+            if (SL.hi[j] == SL.lo[j]) continue;
+            if (!any) { *lo = SL.lo[j]; *hi = SL.hi[j]; any = true; }
+            else { if (SL.lo[j] < *lo) *lo = SL.lo[j]; if (SL.hi[j] > *hi) *hi = SL.hi[j]; }
+        }
+    };
+    const int in_jobs[3] = {0, 2, 4}, aux_jobs[4] = {1, 3, 5, 7};
+    size_t in_lo, in_hi, aux_lo, aux_hi;
+    span(in_jobs, 3, &in_lo, &in_hi);
+    span(aux_jobs, 4, &aux_lo, &aux_hi);
+    const size_t n_in = in_hi - in_lo, n_aux = aux_hi - aux_lo;
     // Device buffers for this proof come out of the grow-only staging area (no cudaMalloc/cudaFree
     // per proof).  The big a, b, c upload runs on a second stream and overlaps the seven
     // multiexps that only need the assignments; the H pipeline waits for it.
-    const size_t dwi = (ni + 63) / 64, dwa = (na + 63) / 64;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes ? bytes : 1, 256); return o; };
     const size_t o_a = carve(m * 32), o_b = carve(m * 32), o_c = carve(m * 32);
-    const size_t o_in = carve(ni * 32), o_aux = carve(na * 32);
-    const size_t o_da = carve(dwa * 8), o_dbi = carve(dwi * 8), o_dba = carve(dwa * 8), o_misc = carve(8192);
+    const size_t o_in = carve(n_in * 32), o_aux = carve(n_aux * 32);
+    // density words per multiexp; jobs that read the same words over the same positions share a buffer
+    size_t o_dens[8];
+    int dens_src[8];
+    for (int j = 0; j < 8; j++) {
+        o_dens[j] = 0;
+        dens_src[j] = -1;
+        if (!SL.dens[j] || SL.hi[j] == SL.lo[j]) continue;
+        dens_src[j] = j;
+        for (int k = 0; k < j; k++)
+            if (dens_src[k] == k && SL.dens[k] == SL.dens[j] && SL.lo[k] == SL.lo[j] && SL.hi[k] == SL.hi[j]) dens_src[j] = k;
+        if (dens_src[j] == j) o_dens[j] = carve((SL.hi[j] - SL.lo[j] + 63) / 64 * 8);
+        else o_dens[j] = o_dens[dens_src[j]];
+    }
+    const size_t o_misc = carve(8192);
     {
         int rr = io_reserve(ctx, off);
         if (rr) return rr;
@@ -797,9 +850,6 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     Fr* d_c = reinterpret_cast<Fr*>(ctx->io + o_c);
     Fr* d_in = reinterpret_cast<Fr*>(ctx->io + o_in);
     Fr* d_aux = reinterpret_cast<Fr*>(ctx->io + o_aux);
-    uint64_t* d_da = reinterpret_cast<uint64_t*>(ctx->io + o_da);
-    uint64_t* d_dbi = reinterpret_cast<uint64_t*>(ctx->io + o_dbi);
-    uint64_t* d_dba = reinterpret_cast<uint64_t*>(ctx->io + o_dba);
     uint8_t* d_misc = reinterpret_cast<uint8_t*>(ctx->io + o_misc);  // partials + vk + r,s + proof
     if (!ctx->copy_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -830,17 +880,21 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         }                          \
     } while (0)
     // small inputs first, on the compute stream
-    if (ni) CKP(cudaMemcpyAsync(d_in, S->input_assignment, ni * 32, cudaMemcpyHostToDevice, st));
-    if (na) CKP(cudaMemcpyAsync(d_aux, S->aux_assignment, na * 32, cudaMemcpyHostToDevice, st));
-    if (dwa) CKP(cudaMemcpyAsync(d_da, S->a_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
-    if (dwi) CKP(cudaMemcpyAsync(d_dbi, S->b_input_density, dwi * 8, cudaMemcpyHostToDevice, st));
-    if (dwa) CKP(cudaMemcpyAsync(d_dba, S->b_aux_density, dwa * 8, cudaMemcpyHostToDevice, st));
+    if (n_in) CKP(cudaMemcpyAsync(d_in, S->input_assignment + 4 * in_lo, n_in * 32, cudaMemcpyHostToDevice, st));
+    if (n_aux) CKP(cudaMemcpyAsync(d_aux, S->aux_assignment + 4 * aux_lo, n_aux * 32, cudaMemcpyHostToDevice, st));
+    for (int j = 0; j < 8; j++)
+        if (dens_src[j] == j)
+            CKP(cudaMemcpyAsync(ctx->io + o_dens[j], SL.dens[j], (SL.hi[j] - SL.lo[j] + 63) / 64 * 8,
+                                cudaMemcpyHostToDevice, st));
     // evaluation vectors on the copy stream
     const Fr* srcs[3] = {(const Fr*)S->a, (const Fr*)S->b, (const Fr*)S->c};
     Fr* dsts[3] = {d_a, d_b, d_c};
-    for (int k = 0; k < 3; k++) {
-        if (nc) CKP(cudaMemcpyAsync(dsts[k], srcs[k], nc * 32, cudaMemcpyHostToDevice, cs));
-        if (m > nc) CKP(cudaMemsetAsync(dsts[k] + nc, 0, (m - nc) * 32, cs));
+    const bool want_h = SL.hi[6] > SL.lo[6];
+    if (want_h) {
+        for (int k = 0; k < 3; k++) {
+            if (nc) CKP(cudaMemcpyAsync(dsts[k], srcs[k], nc * 32, cudaMemcpyHostToDevice, cs));
+            if (m > nc) CKP(cudaMemsetAsync(dsts[k] + nc, 0, (m - nc) * 32, cs));
+        }
     }
     CKP(cudaEventRecord(ctx->copy_done, cs));
 
@@ -855,7 +909,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     uint8_t vkraw[672];
     memcpy(vkraw, P->alpha_g1, 96); memcpy(vkraw + 96, P->beta_g1, 96); memcpy(vkraw + 192, P->delta_g1, 96);
     memcpy(vkraw + 288, P->beta_g2, 192); memcpy(vkraw + 480, P->delta_g2, 192);
-    if (!shard) {
+    if (!partial_mode) {
         CKP(cudaMemcpyAsync(d_vkraw, vkraw, 672, cudaMemcpyHostToDevice, st));
         CKP(cudaMemcpyAsync(d_rs, r, 32, cudaMemcpyHostToDevice, st));
         CKP(cudaMemcpyAsync(d_rs + 1, s, 32, cudaMemcpyHostToDevice, st));
@@ -864,33 +918,21 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     }
 
     // to_le_bits of the assignments (prover.rs:237-250)
-    RCP(fr_pointwise(ctx, 2, d_in, nullptr, ni, st));
-    RCP(fr_pointwise(ctx, 2, d_aux, nullptr, na, st));
+    RCP(fr_pointwise(ctx, 2, d_in, nullptr, n_in, st));
+    RCP(fr_pointwise(ctx, 2, d_aux, nullptr, n_aux, st));
 
-    // the eight multiexps (prover.rs:233,252-307); statuses resolved in the reference's await order
-    size_t b_in_total = 0;
-    for (size_t i = 0; i < ni; i++) b_in_total += (S->b_input_density[i / 64] >> (i % 64)) & 1;
-    size_t boff[8] = {0, ni, 0, b_in_total, 0, b_in_total, 0, 0};
-    size_t h_lo = 0, h_hi = m - 1;
-    if (shard) {
-        for (int j = 0; j < 8; j++) boff[j] = shard->base_offset[j];
-        h_lo = shard->h_lo;
-        h_hi = shard->h_hi;
-        if (h_lo > h_hi || h_hi > m - 1) {
-            cleanup();
-            return BMPC_ERR_INVALID;
-        }
-    }
-    struct Job { const bmpc_bases* bases; size_t off; const uint64_t* sc; size_t n; const uint64_t* dens; void* out; };
+    struct Job { const bmpc_bases* bases; const uint64_t* sc; void* out; };
+    auto in_sc = [&](int j) { return (const uint64_t*)(d_in + (SL.hi[j] > SL.lo[j] ? SL.lo[j] - in_lo : 0)); };
+    auto aux_sc = [&](int j) { return (const uint64_t*)(d_aux + (SL.hi[j] > SL.lo[j] ? SL.lo[j] - aux_lo : 0)); };
     Job jobs[8] = {
-        {P->a, boff[0], (uint64_t*)d_in, ni, nullptr, part_g1 + 0},       // a_inputs   :264-269
-        {P->a, boff[1], (uint64_t*)d_aux, na, d_da, part_g1 + 1},         // a_aux      :270-275
-        {P->b_g1, boff[2], (uint64_t*)d_in, ni, d_dbi, part_g1 + 2},      // b_g1_inputs:285-290
-        {P->b_g1, boff[3], (uint64_t*)d_aux, na, d_dba, part_g1 + 3},     // b_g1_aux   :291-296
-        {P->b_g2, boff[4], (uint64_t*)d_in, ni, d_dbi, part_g2 + 0},      // b_g2_inputs:301-306
-        {P->b_g2, boff[5], (uint64_t*)d_aux, na, d_dba, part_g2 + 1},     // b_g2_aux   :307
-        {P->h, boff[6], (uint64_t*)(d_a + h_lo), h_hi - h_lo, nullptr, part_g1 + 4},   // h :233
-        {P->l, boff[7], (uint64_t*)d_aux, na, nullptr, part_g1 + 5},      // l          :252-257
+        {P->a, in_sc(0), part_g1 + 0},        // a_inputs   :264-269
+        {P->a, aux_sc(1), part_g1 + 1},       // a_aux      :270-275
+        {P->b_g1, in_sc(2), part_g1 + 2},     // b_g1_inputs:285-290
+        {P->b_g1, aux_sc(3), part_g1 + 3},    // b_g1_aux   :291-296
+        {P->b_g2, in_sc(4), part_g2 + 0},     // b_g2_inputs:301-306
+        {P->b_g2, aux_sc(5), part_g2 + 1},    // b_g2_aux   :307
+        {P->h, (const uint64_t*)(d_a + SL.lo[6]), part_g1 + 4},   // h :233
+        {P->l, aux_sc(7), part_g1 + 5},       // l          :252-257
     };
     // All eight are enqueued before anything is awaited, as three chains on three streams, each
     // with its own scratch arena and staging words (slot 0 = the context's own):
@@ -926,7 +968,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         cudaStream_t js = sk ? ctx->slots[sk - 1].stream : st;
         if (sk) swap_slot(sk);
         int rc = BMPC_OK;
-        if (j == 6) {
+        if (j == 6 && want_h) {
             // H polynomial (prover.rs:210-231)
             cudaError_t e_ = cudaStreamWaitEvent(js, ctx->copy_done, 0);
             if (e_ != cudaSuccess) rc = BMPC_ERR_CUDA;
@@ -937,10 +979,12 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
                 rc = h_coefficients_locked(ctx, d_a, d_b, d_c, exp, t1, t2, js);
             }
         }
-        if (!rc)
-            rc = multiexp_enqueue(ctx, jobs[j].bases, jobs[j].off, jobs[j].sc, jobs[j].n, jobs[j].dens, jobs[j].n,
-                                  nullptr, jobs[j].out, js, ctx->h_stage + 256 * j, &pend[j],
-                                  shard ? shard->n_total[j] : 0);
+        if (!rc) {
+            const size_t nj = SL.hi[j] - SL.lo[j];
+            const uint64_t* dj = dens_src[j] >= 0 ? reinterpret_cast<const uint64_t*>(ctx->io + o_dens[j]) : nullptr;
+            rc = multiexp_enqueue(ctx, jobs[j].bases, SL.base_offset[j], jobs[j].sc, nj, dj, nj, nullptr, jobs[j].out,
+                                  js, ctx->h_stage + 256 * j, &pend[j], SL.n_total[j]);
+        }
         if (sk) swap_slot(sk);
         if (rc != BMPC_OK) {      // argument / launch errors; the multiexp statuses come from the flags
             cleanup();
@@ -951,7 +995,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
     CKP(cudaStreamSynchronize(st));
     uint32_t flags[8];
     for (int j = 0; j < 8; j++) statuses[j] = multiexp_collect(pend[j], &flags[j]);
-    if (shard) {   // one rank's share: hand back the partial sums and statuses, the caller gathers them
+    if (partial_mode) {   // one share: hand back the partial sums and raw flags, the caller gathers them
         CKP(cudaMemcpyAsync(ctx->h_stage, part_g1, 2304, cudaMemcpyDeviceToHost, st));
         CKP(cudaStreamSynchronize(st));
         memcpy(partials_out, ctx->h_stage, 6 * sizeof(G1XYZZ));
@@ -983,7 +1027,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
 #undef CKP
 #undef RCP
 }
-}  // namespace
+}  // namespace bmpc
 
 extern "C" {
 int bmpc_create_proof(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
@@ -996,7 +1040,20 @@ int bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_a
                                const bmpc_proof_shard* shard, uint8_t partials_out[BMPC_PROOF_PARTIAL_BYTES],
                                uint32_t flags_out[8]) {
     if (!ctx || !P || !S || !shard || !partials_out || !flags_out) return BMPC_ERR_INVALID;
-    return create_proof_common(ctx, P, S, nullptr, nullptr, shard, nullptr, partials_out, flags_out);
+    // `S` is the rank's slice of the assignment: every multiexp covers all of it
+    ProofSlices sl;
+    const size_t ni = S->num_inputs, na = S->num_aux;
+    const size_t his[8] = {ni, na, ni, na, ni, na, shard->h_hi, na};
+    const uint64_t* ds[8] = {nullptr, S->a_aux_density, S->b_input_density, S->b_aux_density,
+                             S->b_input_density, S->b_aux_density, nullptr, nullptr};
+    for (int j = 0; j < 8; j++) {
+        sl.lo[j] = j == 6 ? shard->h_lo : 0;
+        sl.hi[j] = his[j];
+        sl.base_offset[j] = shard->base_offset[j];
+        sl.n_total[j] = shard->n_total[j];
+        sl.dens[j] = ds[j];
+    }
+    return create_proof_common(ctx, P, S, nullptr, nullptr, &sl, nullptr, partials_out, flags_out);
 }
 
 int bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* P, const uint8_t* partials_all, size_t world,

@@ -42,7 +42,7 @@ struct DomainTables {
 // Tuning knobs read from BMPC_* environment variables ONCE per context (bmpc_ctx_create) and again on
 // bmpc_ctx_reload_env -- not per call.  -1 / 0 = automatic unless noted.
 struct bmpc_tuning {
-    int acc_pairs = -1;            // BMPC_ACC_PAIRS: 0 never, 1 always pair rounds (msm_pairs.cuh)
+    int acc_pairs = 0;             // BMPC_ACC_PAIRS: 0 never (default), 1 always, -1 from pair_min_entries up (msm_pairs.cuh)
     size_t pair_min_entries = (size_t)1 << 22;   // BMPC_PAIR_MIN_ENTRIES
     int pair_k = 0;                // BMPC_PAIR_K: pairs per thread per inversion
     int acc_affine = -1;           // BMPC_ACC_AFFINE: 0 never, 1 always the batched-affine tree
@@ -92,6 +92,11 @@ struct bmpc_ctx {
     // staging for small results
     uint8_t* h_stage = nullptr;  // 4 KB pinned
     uint8_t* d_stage = nullptr;  // 4 KB
+    // lanes of the asynchronous multiexp (multi.cu: bmpc_multiexp_async): child contexts on the same
+    // device, each with its own stream, scratch arena and staging, handed out one per Waiter
+    std::vector<bmpc_ctx*> lanes;
+    std::vector<char> lane_busy;
+    std::mutex lanes_mu;
     std::map<uint32_t, bmpc::DomainTables> domains;
     bmpc::Fr* tw_small[2] = {nullptr, nullptr};  // fwd / inv powers of the 2^SMALL_LOG-th root
     // optional per-kernel timing (bench.py roofline): CUDA event pairs on the launching stream
@@ -357,6 +362,41 @@ struct GroupOps {
     static int precompute_tables(bmpc_ctx* ctx, void* d_tables, size_t n, uint32_t c, uint32_t W,
                                  cudaStream_t st);
 };
+
+// ------------------------------------------------------------------ api.cu
+// A multiexp in flight: everything is enqueued on `st`, the flags word (and the result bytes)
+// land in the pinned staging area at `h`; multiexp_collect turns them into the reference's status
+// once the stream has been synchronised.  create_proof enqueues all eight before waiting once; the
+// asynchronous Waiter of multi.cu keeps one per lane.
+struct MsmPending {
+    cudaStream_t st = nullptr;     // nullptr: nothing was launched (n == 0), status OK
+    const uint8_t* h = nullptr;
+    size_t out_bytes = 0;
+    uint8_t* out = nullptr;
+};
+int flags_to_status(uint32_t flags);
+// n_ref: the length of the WHOLE exponent vector when this call is one shard of it (0: this call is
+// the whole multiexp)
+int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* d_scalars,
+                     size_t n, const uint64_t* d_density, size_t density_len, uint8_t* out, void* d_partial,
+                     cudaStream_t st, uint8_t* h_dst, MsmPending* pend, size_t n_ref = 0);
+int multiexp_collect(const MsmPending& pend, uint32_t* flags_out = nullptr);   // after the stream was synchronised
+int multiexp_dev_locked(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* d_scalars,
+                        size_t n, const uint64_t* d_density, size_t density_len, uint8_t* out, void* d_partial,
+                        cudaStream_t st, size_t n_ref = 0, uint32_t* flags_out = nullptr);
+
+// One device's share of create_proof (multi.cu; the eight multiexps in the order
+// a_inputs, a_aux, b_g1_inputs, b_g1_aux, b_g2_inputs, b_g2_aux, h, l): multiexp j runs over the
+// exponent positions [lo[j], hi[j]) of the FULL input / aux / H vector, starts at base
+// base_offset[j] of the device's slice of the query vector and reads density words re-based to bit
+// 0 of lo[j] (host memory, NULL = FullDensity); n_total[j] = length of the whole exponent vector.
+struct ProofSlices {
+    size_t lo[8], hi[8], base_offset[8], n_total[8];
+    const uint64_t* dens[8];
+};
+int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignment* S, const uint64_t r[4],
+                        const uint64_t s[4], const ProofSlices* slices, uint8_t* proof_out, uint8_t* partials_out,
+                        uint32_t* flags_out);
 
 // ---------------------------------------------------------------- prove.cu
 struct ProveTailArgs {

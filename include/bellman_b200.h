@@ -159,6 +159,19 @@ int  bmpc_msm_geometry(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_
  * blocks, info[4] = threads per block, info[5] = max points per slice */
 int  bmpc_msm_accumulate_info(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, uint32_t info[8]);
 
+/* Asynchronous form -- the reference's Waiter (src/multicore.rs:33-118): `multiexp` returns at once
+ * and prover.rs:233-307 keeps eight of them in flight before the first wait().  The call enqueues
+ * the upload of the scalars and the whole multiexp on a lane of the context (its own stream, scratch
+ * arena and staging; up to 16 lanes, created on first use) and returns; `scalars` / `density_words`
+ * must stay valid until bmpc_waiter_wait.  bmpc_waiter_wait blocks, writes the 96 / 192 result bytes,
+ * returns the multiexp's status (same semantics as bmpc_multiexp) and frees the waiter.  With two or
+ * more in flight the upload of one overlaps the kernels of the other. */
+typedef struct bmpc_waiter bmpc_waiter;
+int  bmpc_multiexp_async(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                         const uint64_t* scalars, size_t n,
+                         const uint64_t* density_words, size_t density_len, bmpc_waiter** out);
+int  bmpc_waiter_wait(bmpc_waiter* w, uint8_t* out);
+
 /* ---- EvaluationDomain  (src/domain.rs:21-189) ------------------------------------------ */
 /* from_coeffs (:47-79): pads with zeros to m = 2^exp >= len (m = 1 for len <= 1);
  * exp >= 32 -> BMPC_ERR_DEGREE_TOO_LARGE.  coeffs: len x 4 u64 Montgomery limbs (host). */
@@ -281,6 +294,53 @@ int  bmpc_create_proof_partials(bmpc_ctx* ctx, const bmpc_params* params, const 
                                 uint32_t flags_out[8]);
 int  bmpc_create_proof_finish(bmpc_ctx* ctx, const bmpc_params* params, const uint8_t* partials_all, size_t world,
                               const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
+/* ---- all GPUs of a node behind one call (SURVEY 8b `bmpc_ctx_create(devices, n)`, 8e) ---------------
+ * The reference's multiexp (multiexp.rs:254-281) and create_proof (prover.rs:176-350) are one call
+ * in one process; bmpc_multi keeps that shape over N devices: one context per device inside, a base
+ * vector split evenly by base index at registration (device g holds bases [g n/N, (g+1) n/N)), and
+ * per call the exponent positions cut so that each device's positions consume exactly its bases
+ * (with a density map: the position of the k-th dense bit, counted on the host), one host thread
+ * per device, the XYZZ partial sums gathered on device 0 by peer copies (cudaMemcpyPeerAsync over
+ * NVLink, 192 / 384 bytes per device) and folded there, and the raw error flags of all shards ORed
+ * before the reference's precedence rule is applied (multiexp.rs:244-249).  Same result bytes and
+ * statuses as the single-device calls.  `devices` may name a device more than once (tests). */
+typedef struct bmpc_multi bmpc_multi;
+typedef struct bmpc_multi_bases bmpc_multi_bases;
+int  bmpc_multi_create(const int* devices, int n, bmpc_multi** out);
+void bmpc_multi_destroy(bmpc_multi* m);
+int  bmpc_multi_size(const bmpc_multi* m);
+bmpc_ctx* bmpc_multi_ctx(bmpc_multi* m, int rank);      /* the per-device context (tuning, profiling) */
+const char* bmpc_multi_last_error(const bmpc_multi* m);
+int  bmpc_multi_bases_register(bmpc_multi* m, int group, const void* points, size_t n, size_t stride,
+                               int form, bmpc_multi_bases** out);
+int  bmpc_multi_bases_precompute(bmpc_multi* m, bmpc_multi_bases* b, int window_bits);
+size_t bmpc_multi_bases_len(const bmpc_multi_bases* b);
+/* device `rank`'s slice and the index of its first base in the whole vector */
+const bmpc_bases* bmpc_multi_bases_part(const bmpc_multi_bases* b, int rank, size_t* first);
+void bmpc_multi_bases_free(bmpc_multi* m, bmpc_multi_bases* b);
+/* multiexp.rs:254-281 over all devices; arguments and statuses as bmpc_multiexp (host pointers) */
+int  bmpc_multi_multiexp(bmpc_multi* m, const bmpc_multi_bases* bases, size_t base_offset,
+                         const uint64_t* scalars, size_t n,
+                         const uint64_t* density_words, size_t density_len, uint8_t* out);
+typedef struct {
+    const bmpc_multi_bases* h;
+    const bmpc_multi_bases* l;
+    const bmpc_multi_bases* a;
+    const bmpc_multi_bases* b_g1;
+    const bmpc_multi_bases* b_g2;
+    uint8_t alpha_g1[96];
+    uint8_t beta_g1[96];
+    uint8_t beta_g2[192];
+    uint8_t delta_g1[96];
+    uint8_t delta_g2[192];
+} bmpc_multi_params;
+/* prover.rs:206-350 over all devices: every device runs its share of the eight multiexps (the H
+ * polynomial is computed on every device: no collective, no longer than computing it once and
+ * scattering it), the 1920 bytes of partial sums per device are folded and the tail runs on device 0.
+ * Same 192 proof bytes and statuses as bmpc_create_proof. */
+int  bmpc_multi_create_proof(bmpc_multi* m, const bmpc_multi_params* params, const bmpc_assignment* asg,
+                             const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
 
 /* ---- Parameters / VerifyingKey wire format  (src/groth16/mod.rs:146-221,261-400) ------------- */
 typedef struct {

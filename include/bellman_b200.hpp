@@ -14,6 +14,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -62,10 +63,21 @@ class Waiter {            // multicore.rs:93-118; wait() yields the Result (thro
 public:
     static Waiter done(T v) { Waiter w; w.value_ = std::move(v); return w; }
     static Waiter failed(std::exception_ptr e) { Waiter w; w.err_ = e; return w; }
-    T wait() { if (err_) std::rethrow_exception(err_); return std::move(value_); }
+    // work still in flight on the GPU: `finish` blocks for it (bmpc_waiter_wait) and yields the value
+    static Waiter pending(std::function<T()> finish) { Waiter w; w.finish_ = std::move(finish); return w; }
+    Waiter() = default;
+    Waiter(Waiter&&) = default;
+    Waiter& operator=(Waiter&&) = default;
+    ~Waiter() { if (finish_) { try { finish_(); } catch (...) {} } }      // a dropped waiter gives its lane back
+    T wait() {
+        if (finish_) { auto f = std::move(finish_); finish_ = nullptr; return f(); }
+        if (err_) std::rethrow_exception(err_);
+        return std::move(value_);
+    }
 private:
     T value_{};
     std::exception_ptr err_;
+    std::function<T()> finish_;
 };
 
 // ---- bases: (Arc<Vec<G::Affine>>, usize) SourceBuilder (multiexp.rs:45-86) --------------------
@@ -158,12 +170,21 @@ Waiter<std::vector<uint8_t>> multiexp(const Worker& pool, const Source& bases, c
                                       const std::vector<Scalar>& exponents) {
     if (density_map.has_query_size() && density_map.get_query_size() != exponents.size())
         throw std::logic_error("assertion failed: query_size == exponents.len()");      // multiexp.rs:273-278
-    std::vector<uint8_t> out(bases.first->group() == BMPC_G1 ? 96 : 192);
-    int st = bmpc_multiexp(pool.ctx(), bases.first->handle(), bases.second,
-                           exponents.empty() ? nullptr : exponents[0].data(), exponents.size(),
-                           density_map.words(), density_map.words() ? exponents.size() : 0, out.data());
+    // Returns at once like the reference (the multiexp runs on a lane of the context); `exponents`
+    // and the density map must outlive wait(), as the Arc<Vec<..>> arguments of the reference do.
+    const size_t nbytes = bases.first->group() == BMPC_G1 ? 96 : 192;
+    bmpc_waiter* h = nullptr;
+    int st = bmpc_multiexp_async(pool.ctx(), bases.first->handle(), bases.second,
+                                 exponents.empty() ? nullptr : exponents[0].data(), exponents.size(),
+                                 density_map.words(), density_map.words() ? exponents.size() : 0, &h);
     try { check(st, pool.ctx()); } catch (...) { return Waiter<std::vector<uint8_t>>::failed(std::current_exception()); }
-    return Waiter<std::vector<uint8_t>>::done(std::move(out));
+    bmpc_ctx* ctx = pool.ctx();
+    auto keep = bases.first;
+    return Waiter<std::vector<uint8_t>>::pending([h, ctx, nbytes, keep]() {
+        std::vector<uint8_t> out(nbytes);
+        check(bmpc_waiter_wait(h, out.data()), ctx);
+        return out;
+    });
 }
 
 // ---- EvaluationDomain<Fr, Scalar<Fr>> (domain.rs:21-189), coefficients resident in HBM ----------

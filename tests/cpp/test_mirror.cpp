@@ -107,6 +107,41 @@ int main() {
         REQUIRE(l1->scalar_mul(mult)->read(0, ln) == Bases::fixed_base_mul(worker, BMPC_G1, gen.data(), prod)->read(0, ln));
     }
 
+    // ---- several multiexps in flight before the first wait() (prover.rs:233-307 / multicore.rs:93-118)
+    {
+        auto w1 = multiexp(worker, Source{bases, 0}, FullDensity{}, s);
+        auto w2 = multiexp(worker, Source{bases, 3}, dens, s2);
+        auto w3 = multiexp(worker, Source{bases, 0}, FullDensity{}, s);
+        REQUIRE(w3.wait() == expect);
+        REQUIRE(w2.wait() == expect2);
+        REQUIRE(w1.wait() == expect);
+    }
+
+    // ---- all devices of the node behind ONE call (SURVEY 8b bmpc_ctx_create(devices, n)): here the
+    // same GPU twice / three times, which runs the whole plan (base split, position cuts through the
+    // density map, peer gather, fold) on a one-GPU box.  Same bytes as the single-device calls.
+    for (int nd = 2; nd <= 3; nd++) {
+        int devs[3] = {0, 0, 0};
+        bmpc_multi* mw = nullptr;
+        REQUIRE(bmpc_multi_create(devs, nd, &mw) == BMPC_OK && bmpc_multi_size(mw) == nd);
+        auto raw = bases->read(0, n);
+        bmpc_multi_bases* mb = nullptr;
+        REQUIRE(bmpc_multi_bases_register(mw, BMPC_G1, raw.data(), n, 96, BMPC_FORM_UNCOMPRESSED_BE, &mb) == BMPC_OK);
+        REQUIRE(bmpc_multi_bases_len(mb) == n);
+        std::vector<uint8_t> out(96);
+        REQUIRE(bmpc_multi_multiexp(mw, mb, 0, s[0].data(), n, nullptr, 0, out.data()) == BMPC_OK);
+        REQUIRE(out == expect);
+        REQUIRE(bmpc_multi_multiexp(mw, mb, 3, s2[0].data(), n - 3, dens.words(), n - 3, out.data()) == BMPC_OK);
+        REQUIRE(out == expect2);
+        REQUIRE(bmpc_multi_bases_precompute(mw, mb, 0) == BMPC_OK);
+        REQUIRE(bmpc_multi_multiexp(mw, mb, 0, s[0].data(), n, nullptr, 0, out.data()) == BMPC_OK);
+        REQUIRE(out == expect);
+        REQUIRE(bmpc_multi_multiexp(mw, mb, 5, s[0].data(), n, nullptr, 0, out.data()) == BMPC_ERR_UNEXPECTED_EOF);
+        REQUIRE(bmpc_multi_multiexp(mw, mb, 0, s[0].data(), n, dens.words(), n - 3, out.data()) == BMPC_ERR_LENGTH_MISMATCH);
+        bmpc_multi_bases_free(mw, mb);
+        bmpc_multi_destroy(mw);
+    }
+
     // ---- fft_composition (domain.rs:427-463)
     for (unsigned logn = 0; logn < 11; logn++) {
         std::vector<Scalar> c(size_t(1) << logn);
