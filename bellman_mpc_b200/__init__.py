@@ -369,6 +369,17 @@ def list_mul_matrix(list_g1, list_g2, matrix):
 
 
 # --------------------------------------------------------------------------- density
+def fold_vectors(pool, vectors, rho):
+    """The GPU half of a ceremony check batched by random linear combination (the reference checks
+    every element of a contribution with two pairings, groth16/mpc.rs:806-862,1065-1131): for each
+    resident vector V returns sum_i rho_i V_i (uncompressed bytes), all multiexps in flight together.
+    The caller draws `rho` (n scalars, canonical (n, 4) u64; 128 random bits each are enough) AFTER it
+    has received the vectors, and finishes with two pairings per pair of folded points."""
+    exps = np.ascontiguousarray(rho, dtype=np.uint64).reshape(-1, 4)
+    waiters = [multiexp(pool, (v, 0), FullDensity(), exps[:len(v)]) for v in vectors]
+    return [w.wait() for w in waiters]
+
+
 class FullDensity:
     """multiexp.rs:95-114"""
 

@@ -31,7 +31,8 @@ EXPORTS = [
     "bmpc_domain_distribute_powers", "bmpc_domain_z", "bmpc_domain_divide_by_z_on_coset",
     "bmpc_domain_mul_assign", "bmpc_domain_sub_assign", "bmpc_ntt_dev", "bmpc_ntt",
     "bmpc_ntt_batch_dev", "bmpc_fr_swap01_dev", "bmpc_ntt_fourstep_twiddle_dev", "bmpc_fr_scale_pow_dev",
-    "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_fr_to_canonical_dev",
+    "bmpc_h_coefficients", "bmpc_h_coefficients_dev", "bmpc_h_coset_evals_dev", "bmpc_h_from_coset_evals_dev",
+    "bmpc_fr_to_canonical_dev",
     "bmpc_create_proof", "bmpc_create_proof_partials", "bmpc_create_proof_finish", "bmpc_batch_scalar_mul", "bmpc_fixed_base_mul",
     "bmpc_list_mul_matrix",
     "bmpc_params_read", "bmpc_params_write", "bmpc_params_free",
@@ -147,6 +148,8 @@ def load():
         "bmpc_h_coefficients": (i32, [vp, vp, vp, vp, sz, vp, C.POINTER(sz)]),
         "bmpc_h_coefficients_dev": (i32, [vp, vp, vp, vp, u32, vp]),
         "bmpc_fr_to_canonical_dev": (i32, [vp, vp, sz, vp]),
+        "bmpc_h_coset_evals_dev": (i32, [vp, vp, u32, vp, sz, vp]),
+        "bmpc_h_from_coset_evals_dev": (i32, [vp, vp, vp, vp, u32, vp]),
         "bmpc_create_proof": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), vp, vp, vp]),
         "bmpc_create_proof_partials": (i32, [vp, C.POINTER(Params), C.POINTER(Assignment), C.POINTER(ProofShard), vp,
                                              C.POINTER(u32 * 8)]),

@@ -396,58 +396,110 @@ struct Field {
         l[N - 1] = t[N - 1] >> 1;
     }
 
-    // Inverse (0 -> 0) by the binary extended Euclidean algorithm on the raw limbs: at most
-    // 2 log2 p iterations of shifts and subtractions (~30 K instructions) instead of the ~570
-    // Montgomery products of the Fermat ladder; it sits on the serial tail of every multiexp
-    // (to_affine) where one thread runs alone.  Vartime, like the reference's `invert` callers here.
+    // Inverse (0 -> 0).  It sits on the serial path of every block-shared batch inversion of the bucket
+    // accumulation (msm_affine.cuh: one thread inverts while the block waits; measured with the
+    // inversion stubbed out: 12.8 % of the accumulate kernel at 2^21 points, 3.9 % at 2^24) and of every
+    // to_affine, so instructions, not products, are what counts.  Kaliski's almost-inverse (1995): the
+    // binary extended Euclid without any modular reduction inside the loop --
+    //     u = p, v = a, r = 0, s = 1;   invariants  a r = -u 2^k,  a s = v 2^k (mod p),  u s + v r = p
+    //     u even: u /= 2, s *= 2 | v even: v /= 2, r *= 2 | u > v: u = (u-v)/2, r += s, s *= 2
+    //     | else: v = (v-u)/2, s += r, r *= 2;   k counts the halvings
+    // -- with every run of trailing zero bits taken in one multi-limb shift.  It ends with
+    // p - r = a^-1 2^k, bits(p) <= k <= 2 bits(p); the power of two goes away in two Montgomery products:
+    // (x R^2 / R) (2^(2 log R - k)) / R = x R^2 / 2^k.  About a third of the instructions of the textbook
+    // binary algorithm it replaces (which halved x1, x2 modulo p at every step).  Vartime, like the
+    // reference's `invert` callers here.
+    BMPC_HD static uint32_t ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)(__ffs((int)x) - 1);
+#else
+        return (uint32_t)__builtin_ctz(x);
+#endif
+    }
+    // x >>= t, 1 <= t <= 31
+    BMPC_HD static void shr_limbs(uint32_t* x, uint32_t t) {
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) x[i] = (x[i] >> t) | (x[i + 1] << (32u - t));
+        x[N - 1] >>= t;
+    }
+    // x <<= t, 1 <= t <= 31 (the caller guarantees no bit is lost)
+    BMPC_HD static void shl_limbs(uint32_t* x, uint32_t t) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) x[i] = (x[i] << t) | (x[i - 1] >> (32u - t));
+        x[0] <<= t;
+    }
     BMPC_COLD Field inv() const {
         if (is_zero()) return *this;
-        uint32_t u[N], v[N];
-        Field x1 = zero(), x2 = zero();
-        x1.l[0] = 1;                               // raw integers, not Montgomery forms
+        uint32_t u[N], v[N], r[N], s[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) { u[i] = l[i]; v[i] = P::mod(i); }
+        for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = l[i]; r[i] = 0; s[i] = 0; }
+        s[0] = 1;
+        uint32_t k = 0;
         for (;;) {
-            uint32_t u_rest = 0, v_rest = 0;
-#pragma unroll
-            for (int i = 1; i < N; i++) { u_rest |= u[i]; v_rest |= v[i]; }
-            if ((u[0] == 1 && u_rest == 0) || (v[0] == 1 && v_rest == 0)) break;
-            while (!(u[0] & 1u)) {
-#pragma unroll
-                for (int i = 0; i < N - 1; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
-                u[N - 1] >>= 1;
-                x1.halve();
+            if (!(u[0] & 1u)) {                    // u > 0 always: a zero low limb is a run of >= 32 zeros
+                const uint32_t t = u[0] ? ctz32(u[0]) : 31u;
+                shr_limbs(u, t);
+                shl_limbs(s, t);
+                k += t;
+                continue;
             }
-            while (!(v[0] & 1u)) {
-#pragma unroll
-                for (int i = 0; i < N - 1; i++) v[i] = (v[i] >> 1) | (v[i + 1] << 31);
-                v[N - 1] >>= 1;
-                x2.halve();
+            if (!(v[0] & 1u)) {
+                const uint32_t t = v[0] ? ctz32(v[0]) : 31u;
+                shr_limbs(v, t);
+                shl_limbs(r, t);
+                k += t;
+                continue;
             }
-            // u >= v ?
-            uint32_t t[N];
-            t[0] = sub_cc(u[0], v[0]);
+            uint32_t d[N];
+            d[0] = sub_cc(u[0], v[0]);
 #pragma unroll
-            for (int i = 1; i < N; i++) t[i] = subc_cc(u[i], v[i]);
-            uint32_t borrow = subc(0, 0);
-            if (!borrow) {
+            for (int i = 1; i < N; i++) d[i] = subc_cc(u[i], v[i]);
+            const uint32_t borrow = subc(0, 0);
+            uint32_t nz = 0;
 #pragma unroll
-                for (int i = 0; i < N; i++) u[i] = t[i];
-                x1 = x1 - x2;
-            } else {
+            for (int i = 0; i < N; i++) nz |= d[i];
+            if (!borrow && nz) {                   // u > v
+#pragma unroll
+                for (int i = 0; i < N; i++) u[i] = d[i];
+                shr_limbs(u, 1);
+                r[0] = add_cc(r[0], s[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) r[i] = addc_cc(r[i], s[i]);
+                r[N - 1] = addc(r[N - 1], s[N - 1]);
+                shl_limbs(s, 1);
+                k++;
+            } else {                                // v >= u
                 v[0] = sub_cc(v[0], u[0]);
 #pragma unroll
                 for (int i = 1; i < N - 1; i++) v[i] = subc_cc(v[i], u[i]);
                 v[N - 1] = subc(v[N - 1], u[N - 1]);
-                x2 = x2 - x1;
+                shr_limbs(v, 1);
+                s[0] = add_cc(s[0], r[0]);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) s[i] = addc_cc(s[i], r[i]);
+                s[N - 1] = addc(s[N - 1], r[N - 1]);
+                shl_limbs(r, 1);
+                k++;
+                if (!nz) break;                     // u == v (== 1, the gcd): v is now 0
             }
         }
-        uint32_t u_rest = 0;
-#pragma unroll
-        for (int i = 1; i < N; i++) u_rest |= u[i];
-        Field x = (u[0] == 1 && u_rest == 0) ? x1 : x2;     // x * (a R) == 1 (mod p)
-        Field r3 = mul_cold(r2(), r2());                      // R^3 (as a raw integer: R^2 * R^2 / R)
-        return mul_cold(x, r3);                               // x R^3 / R = a^-1 R
+        // r < 2 p;  x = p - (r mod p) = a^-1 2^k as a raw integer (a = the raw limbs of *this)
+        Field x;
+        final_sub(x.l, r);
+        x = x.neg();
+        // wanted: (a / R)^-1 R = a^-1 R^2 = x 2^e with e = 2 log2 R - k; the single-limb constant 2^e must
+        // stay below p, i.e. e <= bits(p) - 1 (k within a few bits of its minimum otherwise: double x)
+        uint32_t e = 64u * N - k;
+        while (e >= 32u * N - lead_zero_bits()) { x = x.dbl(); e--; }
+        Field c = zero();
+        c.l[e >> 5] = 1u << (e & 31u);
+        return mul_cold(mul_cold(x, r2()), c);      // (x R^2 / R) 2^e / R = x 2^e
+    }
+    // number of zero bits above the modulus' top bit in its top limb (Fp: 3, Fr: 1)
+    BMPC_HD static constexpr uint32_t lead_zero_bits() {
+        uint32_t t = P::mod(N - 1), z = 0;
+        while (!(t & 0x80000000u)) { t <<= 1; z++; }
+        return z;
     }
 };
 

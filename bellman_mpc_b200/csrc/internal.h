@@ -52,6 +52,7 @@ struct bmpc_tuning {
     int subwindows = 1;            // BMPC_MSM_SUBWINDOWS
     int reduce_block = 0;          // BMPC_REDUCE_BLOCK
     int ntt_no_direct = 0;         // BMPC_NTT_NO_DIRECT
+    int proof_slots = 0;           // BMPC_PROOF_SLOTS: 3 chains of multiexps in create_proof, 8 (one stream each), 0 auto
     void load();
 };
 
@@ -76,7 +77,7 @@ struct bmpc_ctx {
         size_t ws_size = 0;
         uint8_t* d_stage = nullptr;
     };
-    Slot slots[2];
+    Slot slots[7];
     cudaEvent_t inputs_ready = nullptr;
     // Stream contract: the scratch arena, the twiddle / power tables and the staging words are shared
     // per context, so calls on DIFFERENT streams must not overlap.  Every stream-taking entry point
@@ -250,6 +251,9 @@ inline cudaStream_t pick_stream(bmpc_ctx* ctx, void* stream) {
 int ntt_dev_locked(bmpc_ctx* ctx, Fr* d, uint32_t logm, int op, cudaStream_t st);
 int h_coefficients_locked(bmpc_ctx* ctx, Fr* a, Fr* b, Fr* c, uint32_t logm, Fr* t1, Fr* t2,
                           cudaStream_t st);
+int h_coset_evals_locked(bmpc_ctx* ctx, Fr* p, uint32_t logm, Fr* t1, Fr* t2, cudaStream_t st);
+int h_from_coset_evals_locked(bmpc_ctx* ctx, Fr* a, const Fr* b, const Fr* c, uint32_t logm, Fr* t1, Fr* t2,
+                              cudaStream_t st);
 int fr_pointwise(bmpc_ctx* ctx, int what, Fr* a, const Fr* b, size_t n, cudaStream_t st);  // 0 mul 1 sub 2 to_canonical
 int fr_scale_zinv(bmpc_ctx* ctx, Fr* a, size_t m, uint32_t logm, cudaStream_t st);
 int fr_distribute_powers(bmpc_ctx* ctx, Fr* a, size_t m, const Fr* d_g, cudaStream_t st);

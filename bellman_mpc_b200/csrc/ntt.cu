@@ -251,28 +251,41 @@ int ntt_dev_locked(bmpc_ctx* ctx, Fr* d, uint32_t logm, int op, cudaStream_t st)
     return ntt_run(ctx, d, t1, t2, logm, inverse, sc, st);
 }
 
-int h_coefficients_locked(bmpc_ctx* ctx, Fr* a, Fr* b, Fr* c, uint32_t logm, Fr* t1, Fr* t2,
-                          cudaStream_t st) {
-    // prover.rs:214-226 with the O(m) sweeps folded into the transforms:
-    //   P <- iNTT(P) (unscaled); P <- NTT(P_i * g^i / m)        for P in a, b, c
-    //   a <- a*b - c ; a <- iNTT(a) ; a_i <- a_i * g^-i / (m Z(g)), left in canonical form
-    size_t m = (size_t)1 << logm;
+// The H pipeline of prover.rs:214-226 in its two halves (so that several GPUs can share it: one
+// vector each, then one device combines -- bellman_mpc_b200/dist.py):
+//   h_coset_evals_locked:      P <- iNTT(P) (unscaled); P <- NTT(P_i * g^i / m): the evaluations of the
+//                              polynomial through `P` on the coset g <omega>  (ifft + coset_fft)
+//   h_from_coset_evals_locked: a <- a*b - c ; a <- iNTT(a) ; a_i <- a_i * g^-i / (m Z(g)), canonical
+//                              (mul_assign, sub_assign, divide_by_z_on_coset, icoset_fft, to_le_bits)
+// with the O(m) sweeps folded into the transforms.
+int h_coset_evals_locked(bmpc_ctx* ctx, Fr* p, uint32_t logm, Fr* t1, Fr* t2, cudaStream_t st) {
     NttScale inv_plain;
     NttScale coset_fused;
     coset_fused.pre_mode = SCALE_POW;
     coset_fused.pre_kind = K_G_MINV;
-    Fr* polys[3] = {a, b, c};
-    for (int k = 0; k < 3; k++) {
-        int rc = ntt_run(ctx, polys[k], t1, t2, logm, true, inv_plain, st);
-        if (rc) return rc;
-        rc = ntt_run(ctx, polys[k], t1, t2, logm, false, coset_fused, st);
-        if (rc) return rc;
-    }
-    LAUNCH(ctx, fr_mul_sub_kernel, (uint32_t)((m + 255) / 256), 256, 0, st, a, (const Fr*)b, (const Fr*)c, m);
+    int rc = ntt_run(ctx, p, t1, t2, logm, true, inv_plain, st);
+    if (rc) return rc;
+    return ntt_run(ctx, p, t1, t2, logm, false, coset_fused, st);
+}
+
+int h_from_coset_evals_locked(bmpc_ctx* ctx, Fr* a, const Fr* b, const Fr* c, uint32_t logm, Fr* t1, Fr* t2,
+                              cudaStream_t st) {
+    size_t m = (size_t)1 << logm;
+    LAUNCH(ctx, fr_mul_sub_kernel, (uint32_t)((m + 255) / 256), 256, 0, st, a, b, c, m);
     NttScale fin;
     fin.post_mode = SCALE_POW;
     fin.post_kind = K_GINV_MINV_ZINV_CANON;
     return ntt_run(ctx, a, t1, t2, logm, true, fin, st);
+}
+
+int h_coefficients_locked(bmpc_ctx* ctx, Fr* a, Fr* b, Fr* c, uint32_t logm, Fr* t1, Fr* t2,
+                          cudaStream_t st) {
+    Fr* polys[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) {
+        int rc = h_coset_evals_locked(ctx, polys[k], logm, t1, t2, st);
+        if (rc) return rc;
+    }
+    return h_from_coset_evals_locked(ctx, a, b, c, logm, t1, t2, st);
 }
 
 int fr_pointwise(bmpc_ctx* ctx, int what, Fr* a, const Fr* b, size_t n, cudaStream_t st) {

@@ -197,9 +197,11 @@ class ProofShardPlan:
         return sh
 
 
-def proof_partials(worker, params_slice, assignment, plan):
+def proof_partials(worker, params_slice, assignment, plan, skip_h=False):
     """One rank's share: (1920 partial-sum bytes, [8 raw flag words]), or (None, call status) if the
-    call itself failed.  `assignment` is the FULL ProvingAssignment (host); the slices are taken here."""
+    call itself failed.  `assignment` is the FULL ProvingAssignment (host); the slices are taken here.
+    skip_h: leave the H multiexp (and with it the H pipeline and the a, b, c upload) out -- its partial
+    sum comes from `HSplit` then."""
     import ctypes as C
     asg = assignment
     w = worker
@@ -219,6 +221,8 @@ def proof_partials(worker, params_slice, assignment, plan):
     s.a_aux_density, s.b_input_density, s.b_aux_density = ptr(da), ptr(dbi), ptr(db)
     p = params_slice._struct()
     sh = plan.shard_struct()
+    if skip_h:
+        sh.h_hi = sh.h_lo
     out = np.zeros(_lib.PROOF_PARTIAL_BYTES, dtype=np.uint8)
     fl = (C.c_uint32 * 8)()
     rc = w._lib.bmpc_create_proof_partials(w.ctx, C.byref(p), C.byref(s), C.byref(sh),
@@ -253,10 +257,130 @@ def proof_finish(worker, params, gathered_partials, flags_by_rank, r_mont, s_mon
     return rc, (out.tobytes() if rc == _lib.OK else None)
 
 
-def create_proof_sharded(assignment, params_slice, r_mont, s_mont, plan, group=None):
+# The H polynomial shared by the ranks ("compute H once and scatter it").  Recomputing it
+# on every rank costs each of them the whole a, b, c upload (3 x 32 m bytes) and seven transforms
+# before its H multiexp can start: 17 ms of a 30 ms share at 2^22 on 8 GPUs.  Instead the ranks
+# 0 .. min(world, 3) - 1 each take one of a, b, c (ifft + coset_fft of that vector only), the owners of
+# b and c send their coset evaluations to rank 0 (32 m bytes each over NVLink), rank 0 finishes the
+# pipeline (a b - c, divide by Z, icoset_fft, to_le_bits) and sends every rank its slice of the m - 1
+# H scalars.  The seven multiexps that do not need H run meanwhile on every rank.
+H_PARTIAL_OFFSET = 4 * 192          # part_g1[4] = h inside the 1920-byte blob (a_in, a_aux, b1_in, b1_aux, h, l)
+
+
+def h_owner(k, world):
+    """rank that transforms vector k of (a, b, c)"""
+    return k % min(world, 3)
+
+
+class HSplit:
+    """The per-rank steps of the shared H pipeline; the exchange between them is the caller's
+    (torch.distributed send / recv in `create_proof_sharded`, plain lists in the emulated tests).
+    `worker`: a context of its own for these steps -- the rank's main context is busy (and locked)
+    with the other seven multiexps at the same time."""
+
+    def __init__(self, worker, plan, stream=None):
+        self.w, self.plan, self.stream = worker, plan, stream
+        self.log_m = plan.m.bit_length() - 1
+        assert 1 << self.log_m == plan.m
+
+    def coset_evals(self, host_vec, out_tensor):
+        """out_tensor (m x 4 int64, device) <- the coset evaluations of the polynomial through the
+        num_constraints host evaluations `host_vec` (pinned memory keeps the upload asynchronous)"""
+        import ctypes as C
+        hv = np.ascontiguousarray(host_vec, dtype=np.uint64).reshape(-1, 4)
+        rc = self.w._lib.bmpc_h_coset_evals_dev(self.w.ctx, out_tensor.data_ptr(), self.log_m,
+                                                C.c_void_p(hv.ctypes.data), hv.shape[0], self.stream)
+        assert rc == _lib.OK, (rc, self.w._lib.bmpc_last_error(self.w.ctx))
+        return out_tensor
+
+    def combine(self, ea, eb, ec):
+        """rank 0: ea <- canonical H scalars (entries 0 .. m-2) from the three coset evaluations"""
+        rc = self.w._lib.bmpc_h_from_coset_evals_dev(self.w.ctx, ea.data_ptr(), eb.data_ptr(), ec.data_ptr(),
+                                                     self.log_m, self.stream)
+        assert rc == _lib.OK, (rc, self.w._lib.bmpc_last_error(self.w.ctx))
+        return ea
+
+    def h_partial(self, h_bases_slice, h_slice, partial_tensor):
+        """this rank's share of the H multiexp over its slice of the scalars (device tensor):
+        (call status, raw flag word); the XYZZ partial sum is left in partial_tensor (device)"""
+        import ctypes as C
+        fl = C.c_uint32(0)
+        n = self.plan.h_hi - self.plan.h_lo
+        rc = self.w._lib.bmpc_multiexp_shard_dev(self.w.ctx, h_bases_slice.handle, 0, h_slice.data_ptr() if n else None, n,
+                                                 None, 0, self.plan.m - 1, partial_tensor.data_ptr(), C.byref(fl),
+                                                 self.stream)
+        return rc, int(fl.value)
+
+
+def splice_h(partials, flags, h_partial_bytes, h_flags):
+    """put the separately computed H partial sum and flag word into a rank's blob"""
+    b = bytearray(partials)
+    b[H_PARTIAL_OFFSET:H_PARTIAL_OFFSET + 192] = h_partial_bytes
+    f = list(flags)
+    f[6] = h_flags
+    return bytes(b), f
+
+
+def create_proof_sharded(assignment, params_slice, r_mont, s_mont, plan, group=None, h_worker=None):
     """create_proof (prover.rs:206-350) on all ranks of `group`: every rank calls this with its
-    slice of the parameters; every rank gets the 192-byte proof.  One all-gather of 1928 bytes."""
-    partial, flags = proof_partials(params_slice.worker, params_slice, assignment, plan)
+    slice of the parameters; every rank gets the 192-byte proof.  One all-gather of 1928 bytes.
+    h_worker (a second context on the rank's GPU): share the H pipeline between the ranks (`HSplit`)
+    instead of recomputing it everywhere."""
+    w = params_slice.worker
+    if h_worker is None or plan.world < 2:
+        partial, flags = proof_partials(w, params_slice, assignment, plan)
+    else:
+        import threading
+
+        import torch
+        import torch.distributed as dist
+        rank, world, m = plan.rank, plan.world, plan.m
+        dev = torch.device("cuda", w.device)
+        box = {}
+        th = threading.Thread(target=lambda: box.update(r=proof_partials(w, params_slice, assignment, plan, skip_h=True)))
+        th.start()                                        # the seven multiexps that need no H
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            hs = HSplit(h_worker, plan, side.cuda_stream)
+            vecs = (assignment.a, assignment.b, assignment.c)
+            ev = [None, None, None]
+            for k in range(3):
+                if h_owner(k, world) == rank:
+                    ev[k] = hs.coset_evals(vecs[k], torch.empty((m, 4), dtype=torch.int64, device=dev))
+            for k in range(3):                            # owners of b, c (and of a, if not rank 0) -> rank 0
+                o = h_owner(k, world)
+                if o != 0 and rank == o:
+                    dist.send(ev[k], dst=0, group=group)
+                if o != 0 and rank == 0:
+                    ev[k] = torch.empty((m, 4), dtype=torch.int64, device=dev)
+                    dist.recv(ev[k], src=o, group=group)
+            n_h = plan.h_hi - plan.h_lo
+            if rank == 0:
+                h_all = hs.combine(ev[0], ev[1], ev[2])
+                ops = []
+                for g in range(1, world):
+                    lo, hi = shard_range(m - 1, world, g)
+                    if hi > lo:
+                        ops.append(dist.P2POp(dist.isend, h_all[lo:hi], g, group=group))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                h_slice = h_all[plan.h_lo:plan.h_hi]
+            else:
+                h_slice = torch.empty((max(n_h, 1), 4), dtype=torch.int64, device=dev)
+                if n_h:
+                    for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, h_slice[:n_h], 0, group=group)]):
+                        req.wait()
+            hp = torch.zeros(192, dtype=torch.uint8, device=dev)
+            rc_h, fl_h = hs.h_partial(params_slice.h, h_slice, hp)
+            hp_bytes = bytes(hp.cpu().numpy().tobytes())
+        th.join()
+        partial, flags = box["r"]
+        if partial is not None:
+            if rc_h != _lib.OK:
+                partial, flags = None, rc_h
+            else:
+                partial, flags = splice_h(partial, flags, hp_bytes, fl_h)
     rc = _lib.OK
     if partial is None:
         rc, partial, flags = flags, bytes(_lib.PROOF_PARTIAL_BYTES), [0] * 8

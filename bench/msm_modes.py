@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--k", default="256")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--sweep", default="", help="NAME=v1,v2,...: run every mode once per value of this BMPC_* variable")
     args = ap.parse_args()
     w = bm.Worker(0)
     lib = w._lib
@@ -41,7 +42,13 @@ def main():
     optr = out.ctypes.data_as(C.c_void_p)
     st = torch.cuda.Stream()
     res = []
-    for mode in args.modes.split(","):
+    sweep_name, sweep_vals = None, [None]
+    if args.sweep:
+        sweep_name, vals = args.sweep.split("=")
+        sweep_vals = vals.split(",")
+    for mode, sv in [(m, v) for m in args.modes.split(",") for v in sweep_vals]:
+        if sweep_name:
+            os.environ[sweep_name] = sv
         for k in args.k.split(","):
             os.environ["BMPC_ACC_PAIRS"] = "1" if mode == "pairs" else "0"
             os.environ["BMPC_ACC_AFFINE"] = "0" if mode == "xyzz" else "-1"
@@ -70,7 +77,7 @@ def main():
             lib.bmpc_ctx_profile(w.ctx, 0)
             info = (C.c_uint32 * 8)()
             lib.bmpc_msm_accumulate_info(w.ctx, bases.handle, n, C.byref(info))
-            r = {"mode": mode, "k": int(k), "ms": round(ms, 3), "mpts": round(n / ms / 1e3, 1), "ok": bool(ok),
+            r = {"mode": mode, "sweep": f"{sweep_name}={sv}" if sweep_name else None, "k": int(k), "ms": round(ms, 3), "mpts": round(n / ms / 1e3, 1), "ok": bool(ok),
                  "info": list(info)[:6], **prof}
             print(json.dumps(r), flush=True)
             res.append(r)

@@ -112,7 +112,8 @@ class Workload:
     def prove(self):
         if self.world > 1:
             from bellman_mpc_b200 import dist as bdist
-            st, proof = bdist.create_proof_sharded(self.assignment, self.params, self.r, self.s, self.plan)
+            st, proof = bdist.create_proof_sharded(self.assignment, self.params, self.r, self.s, self.plan,
+                                                   h_worker=getattr(self, "h_worker", None))
             assert st == 0, st
             return proof
         return bm.create_proof(self.assignment, self.params, self.r, self.s)
@@ -183,6 +184,12 @@ def prove_bench_sharded(w, log_m, steps, world, rank, precompute=True):
     import torch
     import torch.distributed as dist
     wl = Workload(w, log_m, precompute=precompute, world=world, rank=rank)
+    # a second context on this GPU for the shared H pipeline (bellman_mpc_b200.dist.HSplit); BMPC_H_SPLIT=0:
+    # every rank recomputes H (the round-1 path)
+    import os
+    h_split = os.environ.get("BMPC_H_SPLIT", "1") != "0"
+    if h_split:
+        wl.h_worker = bm.Worker(w.device)
     wl.prove()
     times = []
     proof = None
@@ -201,10 +208,15 @@ def prove_bench_sharded(w, log_m, steps, world, rank, precompute=True):
         "metric": "groth16_prove_seconds", "constraints": 1 << log_m, "value": min(times), "unit": "s",
         "mean_s": sum(times) / len(times), "all_s": [round(t, 4) for t in times], "steps": steps, "n_gpus": world,
         "higher_is_better": False,
-        "timed_region": "prover.rs:206-350 sharded: per rank pinned host a,b,c + its slice of the assignments -> H2D -> "
-                        "7 NTT + 8 partial MSMs -> all-gather of 1928 B -> fold + tail -> 192-byte proof on every rank",
+        "timed_region": ("prover.rs:206-350 sharded: per rank its slice of the assignments -> H2D -> 7 partial MSMs, while "
+                         "ranks 0-2 upload one of a, b, c each (pinned host) and transform it, rank 0 combines them into H and "
+                         "sends every rank its slice -> partial H MSM -> all-gather of 1928 B -> fold + tail -> 192-byte "
+                         "proof on every rank") if h_split else
+                        ("prover.rs:206-350 sharded: per rank pinned host a,b,c + its slice of the assignments -> H2D -> "
+                         "7 NTT + 8 partial MSMs -> all-gather of 1928 B -> fold + tail -> 192-byte proof on every rank"),
+        "h_pipeline": "shared: one vector per rank 0-2, combined on rank 0, slices over NVLink" if h_split else "recomputed on every rank",
         "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": 192 + 1920,
-        "parallelism": f"multiexp exponent ranges split x{world} (aux positions in blocks of 64), H replicated",
+        "parallelism": f"multiexp exponent ranges split x{world} (aux positions in blocks of 64)",
         "crs_setup_s": round(wl.crs_setup_s, 2),
     }
     if rank == 0:

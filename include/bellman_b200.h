@@ -233,6 +233,18 @@ int  bmpc_h_coefficients(bmpc_ctx* ctx, const uint64_t* a, const uint64_t* b, co
  * are clobbered; the m-1 canonical scalars are left in d_a. */
 int  bmpc_h_coefficients_dev(bmpc_ctx* ctx, uint64_t* d_a, uint64_t* d_b, uint64_t* d_c,
                              uint32_t log_m, void* stream);
+/* The same pipeline in its two halves, so that several GPUs can share it (one vector each, one device
+ * combines; bellman_mpc_b200/dist.py):
+ *   bmpc_h_coset_evals_dev: d_p (m Montgomery evaluations, padded) <- ifft, coset_fft (prover.rs:214-219
+ *     for one of a, b, c): the polynomial's evaluations on the coset; host_src != NULL: the host_len
+ *     evaluations are first uploaded from there and padded with zeros to m (from_coeffs, :211-213);
+ *   bmpc_h_from_coset_evals_dev: d_a <- (d_a * d_b - d_c) / Z on the coset, icoset_fft, to_le_bits
+ *     (prover.rs:221-231): the m-1 canonical H scalars are left in d_a (entry m-1 is dropped by the caller).
+ * bmpc_h_coefficients_dev == three times the first, then the second. */
+int  bmpc_h_coset_evals_dev(bmpc_ctx* ctx, uint64_t* d_p, uint32_t log_m, const uint64_t* host_src,
+                            size_t host_len, void* stream);
+int  bmpc_h_from_coset_evals_dev(bmpc_ctx* ctx, uint64_t* d_a, const uint64_t* d_b, const uint64_t* d_c,
+                                 uint32_t log_m, void* stream);
 /* Montgomery -> canonical (PrimeFieldBits::to_le_bits, prover.rs:231,241,248), in place */
 int  bmpc_fr_to_canonical_dev(bmpc_ctx* ctx, uint64_t* d_vals, size_t n, void* stream);
 

@@ -181,6 +181,10 @@ extern "C" {
                                out: *mut u64, out_len: *mut usize) -> c_int;
     pub fn bmpc_h_coefficients_dev(ctx: *mut bmpc_ctx, d_a: *mut u64, d_b: *mut u64, d_c: *mut u64, log_m: u32,
                                    stream: *mut c_void) -> c_int;
+    pub fn bmpc_h_coset_evals_dev(ctx: *mut bmpc_ctx, d_p: *mut u64, log_m: u32, host_src: *const u64, host_len: usize,
+                                  stream: *mut c_void) -> c_int;
+    pub fn bmpc_h_from_coset_evals_dev(ctx: *mut bmpc_ctx, d_a: *mut u64, d_b: *const u64, d_c: *const u64, log_m: u32,
+                                       stream: *mut c_void) -> c_int;
     pub fn bmpc_fr_to_canonical_dev(ctx: *mut bmpc_ctx, d_vals: *mut u64, n: usize, stream: *mut c_void) -> c_int;
     pub fn bmpc_create_proof(ctx: *mut bmpc_ctx, params: *const bmpc_params, asg: *const bmpc_assignment,
                              r: *const u64, s: *const u64, proof_out: *mut u8) -> c_int;

@@ -160,3 +160,48 @@ def test_sharded_create_proof_emulated(worker, world):
     for wl in keep:
         wl.free()
     full.free()
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_sharded_create_proof_shared_h_emulated(worker, world):
+    """The H polynomial computed once by the ranks together (dist.HSplit: one of a, b, c per rank 0..2,
+    combined on rank 0, every rank gets its slice of the scalars and runs its share of the H multiexp) and
+    the other seven multiexps per rank without H: same 192 bytes as the single-GPU call.  Ranks run one
+    after the other on this GPU; sends and receives are tensor hand-overs."""
+    import torch
+    import bench_prove
+    from bellman_mpc_b200 import dist as bdist
+    log_m = 10
+    full = bench_prove.Workload(worker, log_m)
+    expect = full.prove()
+    assert expect == full.expected_proof()
+    hw = bm.Worker(0)
+    wls = [bench_prove.Workload(worker, log_m, world=world, rank=r) for r in range(world)]
+    m = wls[0].plan.m
+    # coset evaluations by their owners, then rank 0 combines
+    ev = [None] * 3
+    for k, name in enumerate(("a", "b", "c")):
+        o = bdist.h_owner(k, world)
+        hs = bdist.HSplit(hw, wls[o].plan)
+        ev[k] = hs.coset_evals(getattr(wls[o].assignment, name), torch.empty((m, 4), dtype=torch.int64, device="cuda"))
+    h_all = bdist.HSplit(hw, wls[0].plan).combine(ev[0], ev[1], ev[2])
+    torch.cuda.synchronize()
+    # == the host-buffer H pipeline
+    want_h = bm.h_coefficients(worker, full.a, full.b, full.c)
+    assert np.array_equal(h_all[:m - 1].cpu().numpy().view(np.uint64), want_h)
+    parts, flags = [], []
+    for r, wl in enumerate(wls):
+        pb, fl = bdist.proof_partials(worker, wl.params, wl.assignment, wl.plan, skip_h=True)
+        assert pb is not None, fl
+        hp = torch.zeros(192, dtype=torch.uint8, device="cuda")
+        rc, fh = bdist.HSplit(hw, wl.plan).h_partial(wl.params.h, h_all[wl.plan.h_lo:wl.plan.h_hi].contiguous(), hp)
+        assert rc == 0
+        pb, fl = bdist.splice_h(pb, fl, bytes(hp.cpu().numpy().tobytes()), fh)
+        parts.append(pb)
+        flags.append(fl)
+    rc, proof = bdist.proof_finish(worker, wls[0].params, parts, flags, full.r, full.s)
+    assert rc == 0 and proof == expect
+    for wl in wls:
+        wl.free()
+    full.free()
+    hw.close()

@@ -47,6 +47,31 @@ def test_field_ops(lib, which):
         assert _v(out) == R * R * pow(a, -1, p) % p
 
 
+@pytest.mark.parametrize("which", ["fr", "fp"])
+def test_inversion(lib, which):
+    """Field::inv (Kaliski almost-inverse + two Montgomery products, field.cuh) against pow(a, -1, p):
+    small values (k at its minimum: the doubling fix-up), powers of two and values with long runs of zero
+    bits (multi-bit shifts, a zero low limb), p - 1, R, R^-1, and random elements; inv(0) = 0."""
+    F, fn, n = (fields.Fr, lib.hc_fr_op, 8) if which == "fr" else (fields.Fp, lib.hc_fp_op, 12)
+    p, R = F.p, F.R
+    rng = random.Random(5)
+    cases = [1, 2, 3, p - 1, p - 2, R % p, R * R % p, pow(R, -1, p), 1 << 31, 1 << 32, 1 << 64, 1 << 96,
+             1 << (p.bit_length() - 1), p >> 1, (p >> 1) + 1]
+    cases += [rng.randrange(1, p) for _ in range(1500)]
+    cases += [rng.randrange(1, 1 << 40) for _ in range(100)]
+    cases += [(rng.randrange(1, p) >> rng.randrange(1, 200)) << rng.randrange(0, 100) for _ in range(200)]
+    for a in cases:
+        a %= p
+        if not a:
+            continue
+        out = (ctypes.c_uint32 * n)()
+        fn(4, _l(a, n), _l(0, n), out)
+        assert _v(out) == R * R * pow(a, -1, p) % p, (which, hex(a))
+    out = (ctypes.c_uint32 * n)()
+    fn(4, _l(0, n), _l(0, n), out)
+    assert _v(out) == 0
+
+
 def test_group_law(lib):
     P, R = fields.Fp.p, fields.Fp.R
     Ri = pow(R, -1, P)

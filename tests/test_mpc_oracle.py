@@ -50,3 +50,34 @@ def test_list_mul_matrix_index_panics():
         mpc.list_mul_matrix(G, [1, 2], [[(1, 0)], [(1, 1)], [(1, 0)]])      # taller than the list
     with pytest.raises(IndexError):
         mpc.list_mul_matrix(G, [1, 2], [[(1, 2)]])                           # column out of range
+
+
+def test_contribution_checks_dummy_and_bls():
+    """verify_new_paramter (mpc.rs:787-804) and the per-element loops of verify_uncommon_paramter
+    (:1091-1124) with the oracle pairings; the folded form accepts and rejects the same cases."""
+    from oracle import groth16 as og
+    rng = random.Random(12)
+    for E in (og.DUMMY, og.BLS12):
+        q = E.Fr.p
+        G1, G2 = E.G1, E.G2
+        base, mine = rng.randrange(1, q), rng.randrange(1, q)
+        pair = mpc.ParameterPair(G1.mul(G1.gen, base * mine % q), G2.mul(G2.gen, base * mine % q),
+                                 G1.mul(G1.gen, mine), G2.mul(G2.gen, mine))
+        assert mpc.verify_new_parameter(E, pair, G1.mul(G1.gen, base), G2.mul(G2.gen, base))
+        bad = mpc.ParameterPair(pair.g1_result, G2.mul(G2.gen, (base * mine + 1) % q), pair.g1_mine, pair.g2_mine)
+        assert not mpc.verify_new_parameter(E, bad, G1.mul(G1.gen, base), G2.mul(G2.gen, base))
+        # l against delta: new[i] = matrixed[i] / delta
+        n = 3
+        delta = rng.randrange(1, q)
+        ms = [rng.randrange(1, q) for _ in range(n)]
+        matrixed = [G1.mul(G1.gen, m) for m in ms]
+        new = [G1.mul(G1.gen, m * pow(delta, -1, q) % q) for m in ms]
+        d2 = G2.mul(G2.gen, delta)
+        assert mpc.verify_vector(E, new, d2, matrixed)
+        rho = [rng.randrange(1 << 128) % q for _ in range(n)]
+        fold = lambda pts: G1.sum([G1.mul(p, r) for p, r in zip(pts, rho)]) if E is og.BLS12 else \
+            sum(p * r for p, r in zip(pts, rho)) % q
+        assert mpc.verify_vector_folded(E, fold(new), d2, fold(matrixed))
+        new[1] = G1.add(new[1], G1.gen)
+        assert not mpc.verify_vector(E, new, d2, matrixed)
+        assert not mpc.verify_vector_folded(E, fold(new), d2, fold(matrixed))
