@@ -203,6 +203,7 @@ template <class F>
 size_t GroupOps<F>::curve_bytes_xyzz(const MsmPlan& p) {
     return ws_need(p.max_tasks, sizeof(XYZZ<F>)) + 2 * ws_need((size_t)p.g.H * p.nblk, sizeof(XYZZ<F>)) +
            2 * ws_need((size_t)p.g.H * (p.nblk / BMPC_FOLD_GROUP + 1), sizeof(XYZZ<F>)) +
+           2 * ws_need((size_t)p.g.H * (p.nblk / (BMPC_FOLD_GROUP * BMPC_FOLD_GROUP) + 2), sizeof(XYZZ<F>)) +
            ws_need(p.g.H, sizeof(XYZZ<F>)) + ws_need(64, 4) + 1024;
 }
 
@@ -218,9 +219,11 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
     const uint32_t groups = p.nblk > BMPC_FINAL_THREADS ? p.nblk / BMPC_FOLD_GROUP : 0;
     XYZZ<F>* grp_V = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / BMPC_FOLD_GROUP + 1));
     XYZZ<F>* grp_R = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / BMPC_FOLD_GROUP + 1));
+    XYZZ<F>* grp2_V = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / (BMPC_FOLD_GROUP * BMPC_FOLD_GROUP) + 2));
+    XYZZ<F>* grp2_R = ws_take<XYZZ<F>>(ctx, (size_t)g.H * (p.nblk / (BMPC_FOLD_GROUP * BMPC_FOLD_GROUP) + 2));
     XYZZ<F>* win = ws_take<XYZZ<F>>(ctx, g.H);
     uint32_t* ticket = ws_take<uint32_t>(ctx, 64);
-    if (!partials || !blk_V || !blk_R || !grp_V || !grp_R || !win || !ticket) {
+    if (!partials || !blk_V || !blk_R || !grp_V || !grp_R || !grp2_V || !grp2_R || !win || !ticket) {
         ctx->err = "msm workspace carve failed (curve)";
         return BMPC_ERR_INVALID;
     }
@@ -294,23 +297,46 @@ int GroupOps<F>::msm_finish(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* b
                blk_V, blk_R);
     }
     {
-        size_t smem = (size_t)BMPC_FINAL_THREADS * sizeof(XYZZ<F>);
-        CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaMemsetAsync(ticket, 0, 4, st));
         uint32_t m_log = p.s_log, rb = p.rblock;
         while (rb > 1) { m_log++; rb >>= 1; }
         const XYZZ<F>*fin_V = blk_V, *fin_R = blk_R;
         uint32_t fin_n = p.nblk;
-        if (groups) {
-            size_t fsmem = (size_t)BMPC_FOLD_GROUP * sizeof(XYZZ<F>);
-            dim3 fgrid(groups, g.H);
-            LAUNCH(ctx, msm_fold_kernel<F>, fgrid, BMPC_FOLD_GROUP, fsmem, st, (const XYZZ<F>*)blk_V,
-                   (const XYZZ<F>*)blk_R, p.nblk, m_log, grp_V, grp_R);
-            for (uint32_t q = BMPC_FOLD_GROUP; q > 1; q >>= 1) m_log++;
-            fin_V = grp_V; fin_R = grp_R; fin_n = groups;
+        // G1: four lanes per element (quad.cuh): fold in groups of 32 until at most 64 results are left,
+        // then the final step; BMPC_TAIL_QUAD=0 or G2 (an Fp2 quad body would live in local memory):
+        // one thread per element, one fold when a set has more than 256 block results
+        const bool quad = sizeof(F) == sizeof(Fp) && ctx->tune.tail_quad != 0 && (p.nblk & (p.nblk - 1)) == 0;
+        if (quad) {
+            XYZZ<F>* outV[2] = {grp_V, grp2_V};
+            XYZZ<F>* outR[2] = {grp_R, grp2_R};
+            int lvl = 0;
+            while (fin_n > 64) {
+                const uint32_t ng = fin_n / BMPC_FOLD_GROUP;
+                dim3 fgrid(ng, g.H);
+                LAUNCH(ctx, msm_fold_quad_kernel<F>, fgrid, 4 * BMPC_FOLD_GROUP, BMPC_FOLD_GROUP * sizeof(XYZZ<F>), st,
+                       fin_V, fin_R, fin_n, m_log, outV[lvl & 1], outR[lvl & 1]);
+                for (uint32_t q = BMPC_FOLD_GROUP; q > 1; q >>= 1) m_log++;
+                fin_V = outV[lvl & 1]; fin_R = outR[lvl & 1]; fin_n = ng;
+                lvl++;
+            }
+            uint32_t cnt = 8;
+            while (cnt < fin_n) cnt <<= 1;
+            LAUNCH(ctx, msm_final_quad_kernel<F>, g.H, 4 * cnt, cnt * sizeof(XYZZ<F>), st, fin_V, fin_R, g.H, fin_n, m_log,
+                   g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
+        } else {
+            size_t smem = (size_t)BMPC_FINAL_THREADS * sizeof(XYZZ<F>);
+            CK(cudaFuncSetAttribute(msm_final_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (groups) {
+                size_t fsmem = (size_t)BMPC_FOLD_GROUP * sizeof(XYZZ<F>);
+                dim3 fgrid(groups, g.H);
+                LAUNCH(ctx, msm_fold_kernel<F>, fgrid, BMPC_FOLD_GROUP, fsmem, st, (const XYZZ<F>*)blk_V,
+                       (const XYZZ<F>*)blk_R, p.nblk, m_log, grp_V, grp_R);
+                for (uint32_t q = BMPC_FOLD_GROUP; q > 1; q >>= 1) m_log++;
+                fin_V = grp_V; fin_R = grp_R; fin_n = groups;
+            }
+            LAUNCH(ctx, msm_final_kernel<F>, g.H, BMPC_FINAL_THREADS, smem, st, fin_V, fin_R,
+                   g.H, fin_n, m_log, g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
         }
-        LAUNCH(ctx, msm_final_kernel<F>, g.H, BMPC_FINAL_THREADS, smem, st, fin_V, fin_R,
-               g.H, fin_n, m_log, g.c, mode, win, ticket, d_out_bytes, reinterpret_cast<XYZZ<F>*>(d_out_xyzz));
     }
     return BMPC_OK;
 }

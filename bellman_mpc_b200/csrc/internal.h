@@ -52,6 +52,7 @@ struct bmpc_tuning {
     int subwindows = 1;            // BMPC_MSM_SUBWINDOWS
     int reduce_block = 0;          // BMPC_REDUCE_BLOCK
     int ntt_no_direct = 0;         // BMPC_NTT_NO_DIRECT
+    int tail_quad = 1;             // BMPC_TAIL_QUAD: fold / final steps of the bucket reduction with four lanes per element (G1)
     int proof_slots = 0;           // BMPC_PROOF_SLOTS: 3 chains of multiexps in create_proof, 8 (one stream each), 0 auto
     void load();
 };
