@@ -121,10 +121,10 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
         // with every resident warp busy; the same levels cost a product's latency only in
         // msm_fold_kernel (single warps spread over the SMs), so the blocks are kept small and the
         // fold + final kernels take the upper levels.  BMPC_REDUCE_BLOCK: tuning knob.
-        // G2 keeps 256-thread blocks and no fold: its additions are three times as deep, the final
-        // kernel is latency-bound either way, and the extra fold levels and doublings cost more than
-        // the smaller blocks save (measured per G2 multiexp of the 2^22 proof: 4.19 -> 4.70 ms).
-        uint32_t rb = bases->group == BMPC_G1 ? 32 : 256;   // measured (G1, 2^19 buckets): 32 -> 2.38 ms, 64 -> 2.47, 128 -> 2.50, 256 -> 2.58 for combine + reduce + fold + final
+        // Measured (2^19 buckets, combine + reduce + fold + final): G1 32 -> 2.38 ms, 64 -> 2.47, 128 -> 2.50,
+        // 256 -> 2.58; G2 with the four-lane fold / final steps 32 -> 6.40 ms, 256 -> 7.43 (8.21 with
+        // one-thread steps, where 256-thread blocks and no fold were the better choice).
+        uint32_t rb = (bases->group == BMPC_G1 || ctx->tune.tail_quad != 0) ? 32 : 256;
         {
             uint32_t v = (uint32_t)ctx->tune.reduce_block;
             if (v == 32 || v == 64 || v == 128 || v == 256) rb = v;
