@@ -136,6 +136,13 @@ BMPC_HD AffEntries aff_pair_entries(const AffJob<F>& J, uint32_t g, uint32_t i) 
     e.y = aff_ldg_u32(J.sorted + J.start[g] + 2 * i + 1);
     return e;
 }
+// the same with the slice's first entry already in a register
+BMPC_HD AffEntries aff_pair_entries_at(const uint32_t* sorted, uint32_t start, uint32_t i) {
+    AffEntries e;
+    e.x = aff_ldg_u32(sorted + start + 2 * i);
+    e.y = aff_ldg_u32(sorted + start + 2 * i + 1);
+    return e;
+}
 template <class F>
 BMPC_HD Affine<F> aff_fetch_e(const AffJob<F>& J, bool r0, uint32_t e, const Affine<F>* src, uint32_t sH, uint32_t g,
                               uint32_t idx) {
@@ -194,16 +201,21 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
 #pragma unroll 1
         for (uint32_t g = 0; g < G; g++) maxlen = J.len[g] > maxlen ? J.len[g] : maxlen;
         if (!coop.any(r0 || maxlen > 1)) break;
-        // cursor over the pairs (g, i), i < len[g] / 2
+        // cursor over the pairs (g, i), i < len[g] / 2.  The job descriptor lives in local memory (it is
+        // indexed by g), so the current slice's pair count and first entry are kept in registers and
+        // re-read only when the cursor moves to another slice: the per-pair `J.len[g]` / `J.start[g]`
+        // loads were 40 % of the kernel's long-scoreboard stall samples (ncu source view, round 2).
         uint32_t g = 0, i = 0;
         while (g < G && (J.len[g] >> 1) == 0) g++;
+        uint32_t half = 0, st0 = 0;
+        if (g < G) { half = J.len[g] >> 1; st0 = J.start[g]; }
         while (coop.any(g < G)) {
             // ---- forward: denominators and their running product
             F acc = F::one();
             uint32_t cnt = 0;
 #pragma unroll 1
             AffEntries e = {0u, 0u};
-            if (r0 && g < G) e = aff_pair_entries<F>(J, g, i);
+            if (r0 && g < G) e = aff_pair_entries_at(J.sorted, st0, i);
 #pragma unroll 1
             while (cnt < K && g < G) {
                 const uint32_t gc = g, ic = i;          // the current pair; (g, i) moves on to the next
@@ -211,8 +223,12 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
                 F x2 = aff_fetch_x_e<F>(J, r0, e.y, src, sH, gc, 2 * ic + 1);
                 const AffEntries ec = e;
                 i++;
-                while (g < G && i >= (J.len[g] >> 1)) { g++; i = 0; }
-                if (r0 && g < G) e = aff_pair_entries<F>(J, g, i);
+                if (i >= half) {
+                    do { g++; } while (g < G && (J.len[g] >> 1) == 0);
+                    i = 0;
+                    if (g < G) { half = J.len[g] >> 1; st0 = J.start[g]; }
+                }
+                if (r0 && g < G) e = aff_pair_entries_at(J.sorted, st0, i);
                 F d = x2 - x1;
                 bool use = true;
                 if (d.is_zero() || x1.is_zero() || x2.is_zero()) {       // rare
@@ -226,14 +242,15 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
             }
             F inv = coop.invert(acc);
             // ---- backward: walk the same pairs in reverse
-            uint32_t g2 = g, i2 = i;
+            uint32_t g2 = g, i2 = i, st2 = st0;
             if (cnt) {                                   // step back onto the chunk's last pair
                 if (i2 == 0) {
                     do { g2--; } while ((J.len[g2] >> 1) == 0);
                     i2 = J.len[g2] >> 1;
+                    st2 = J.start[g2];
                 }
                 i2--;
-                if (r0) e = aff_pair_entries<F>(J, g2, i2);
+                if (r0) e = aff_pair_entries_at(J.sorted, st2, i2);
             }
 #pragma unroll 1
             for (uint32_t k = cnt; k-- > 0;) {
@@ -244,9 +261,10 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
                     if (i2 == 0) {
                         do { g2--; } while ((J.len[g2] >> 1) == 0);
                         i2 = J.len[g2] >> 1;
+                        st2 = J.start[g2];
                     }
                     i2--;
-                    if (r0) e = aff_pair_entries<F>(J, g2, i2);
+                    if (r0) e = aff_pair_entries_at(J.sorted, st2, i2);
                 }
                 F d;
                 int kind = aff_classify<F>(P, Q, d);
@@ -300,6 +318,15 @@ BMPC_HD void aff_run_job(AffJob<F>& J, F* pre, uint32_t K, XYZZ<F>* partials, co
 // trees, node n has children 2n and 2n+1, leaves at B + thread).
 template <class F>
 struct BlockCoop {
+    // The 14 products per thread per chunk of the product tree.  G2: out of line -- fully inlined the
+    // G2 kernel is 265 KB of code and `no_instruction` is its top stall (ncu, profiles/r02_*_g2_*: 4.4
+    // cycles per issue); without the tree's two Fp2 sites it is 197 KB and 4.5 % faster (2^21 points:
+    // 31.5 -> 30.1 ms; the forward pass' product out of line as well: 32.4 ms, worse).  G1 (108 KB, no
+    // instruction starvation) keeps them inlined: 0.3 % faster.
+    static __device__ __forceinline__ F mul_rare(const F& a, const F& b) {
+        if constexpr (sizeof(F) > sizeof(Fp)) return F::mul_cold(a, b);
+        else return a * b;
+    }
     F* P;
     F* I;
     uint32_t B;   // threads per block, power of two
@@ -310,7 +337,7 @@ struct BlockCoop {
         __syncthreads();
 #pragma unroll 1
         for (uint32_t w = B >> 1; w >= 1; w >>= 1) {
-            if (j < w) P[w + j] = P[2 * (w + j)] * P[2 * (w + j) + 1];
+            if (j < w) P[w + j] = mul_rare(P[2 * (w + j)], P[2 * (w + j) + 1]);
             __syncthreads();
         }
         if (j == 0) I[1] = P[1].inv();
@@ -319,7 +346,7 @@ struct BlockCoop {
         for (uint32_t w = 1; w < B; w <<= 1) {
             if (j < 2 * w) {
                 uint32_t c = 2 * w + j;
-                I[c] = I[c >> 1] * P[c ^ 1u];
+                I[c] = mul_rare(I[c >> 1], P[c ^ 1u]);
             }
             __syncthreads();
         }

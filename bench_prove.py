@@ -120,7 +120,11 @@ class Workload:
 
     def h2d_bytes(self):
         p = self.plan
-        return (32 * (3 * self.m + (p.in_hi - p.in_lo) + (p.aux_hi - p.aux_lo)) + 3 * ((p.aux_hi - p.aux_lo + 63) // 64) * 8
+        vecs = 3                      # a, b, c uploaded by this rank
+        if self.world > 1 and getattr(self, "h_worker", None) is not None:
+            from bellman_mpc_b200 import dist as bdist
+            vecs = sum(1 for k in range(3) if bdist.h_owner(k, self.world) == self.rank)
+        return (32 * (vecs * self.m + (p.in_hi - p.in_lo) + (p.aux_hi - p.aux_lo)) + 3 * ((p.aux_hi - p.aux_lo + 63) // 64) * 8
                 + self.world * 1928)
 
     def free(self):
