@@ -103,6 +103,11 @@ struct bmpc_multi {
     std::vector<bmpc_ctx*> ctx;
     std::vector<void*> d_part;        // per device: room for one XYZZ partial (512 B)
     void* d_gather = nullptr;         // device 0: one partial per device
+    // the H polynomial shared between the devices (bmpc_multi_create_proof): a second context per device
+    // (its main one is busy with the other seven multiexps meanwhile) and buffers of m coefficients
+    std::vector<bmpc_ctx*> hctx;
+    std::vector<std::vector<void*>> d_ev;   // [device][slot]: slots 0..2 on device 0, slot 0 elsewhere
+    size_t ev_bytes = 0;
     std::string err;
     std::mutex mu;
 };
@@ -257,6 +262,7 @@ int bmpc_multi_create(const int* devices, int n, bmpc_multi** out) {
         DeviceGuard dg(devices[0]);
         if (cudaMalloc(&m->d_gather, 512 * (size_t)n) != cudaSuccess) { bmpc_multi_destroy(m); return BMPC_ERR_CUDA; }
     }
+    m->d_ev.assign((size_t)n, std::vector<void*>());
     *out = m;
     return BMPC_OK;
 }
@@ -268,6 +274,12 @@ void bmpc_multi_destroy(bmpc_multi* m) {
         if (g < m->d_part.size() && m->d_part[g]) cudaFree(m->d_part[g]);
         if (g == 0 && m->d_gather) cudaFree(m->d_gather);
     }
+    for (size_t g = 0; g < m->d_ev.size(); g++) {
+        DeviceGuard dg(m->ctx[g]->device);
+        for (void* p : m->d_ev[g])
+            if (p) cudaFree(p);
+    }
+    for (bmpc_ctx* c : m->hctx) bmpc_ctx_destroy(c);
     for (bmpc_ctx* c : m->ctx) bmpc_ctx_destroy(c);
     delete m;
 }
@@ -442,6 +454,13 @@ int bmpc_multi_create_proof(bmpc_multi* m, const bmpc_multi_params* MP, const bm
     std::vector<uint8_t> partials(G * BMPC_PROOF_PARTIAL_BYTES);
     std::vector<uint32_t> flags(G * 8, 0);
     std::vector<bmpc_params> P(G);
+    // With two or more devices the H polynomial (prover.rs:210-231) is computed ONCE between them
+    // instead of on every device (each would upload all of a, b, c and run seven transforms before its
+    // H multiexp can start): devices 0 .. min(G, 3) - 1 each take one of a, b, c (upload, ifft,
+    // coset_fft), device 0 pulls the other two coset evaluations over NVLink, finishes the pipeline and
+    // every device pulls its slice of the m - 1 scalars for its share of the H multiexp -- all on second
+    // contexts, under the other seven multiexps.
+    const bool share_h = G >= 2 && mm >= 2;
     auto share = [&](size_t g) {
         bmpc_params& p = P[g];
         p.h = MP->h->part[g]; p.l = MP->l->part[g]; p.a = MP->a->part[g];
@@ -453,6 +472,7 @@ int bmpc_multi_create_proof(bmpc_multi* m, const bmpc_multi_params* MP, const bm
         for (int j = 0; j < 8; j++) {
             sl.lo[j] = cuts[j].cut[g];
             sl.hi[j] = cuts[j].cut[g + 1];
+            if (j == 6 && share_h) sl.hi[j] = sl.lo[j];        // H comes from the shared pipeline below
             sl.base_offset[j] = cuts[j].base_off[g];
             sl.n_total[j] = cnt[j];
             sl.dens[j] = nullptr;
@@ -471,11 +491,121 @@ int bmpc_multi_create_proof(bmpc_multi* m, const bmpc_multi_params* MP, const bm
         rcs[g] = create_proof_common(m->ctx[g], &p, S, nullptr, nullptr, &sl, nullptr,
                                      partials.data() + g * BMPC_PROOF_PARTIAL_BYTES, flags.data() + 8 * g);
     };
+    std::vector<std::thread> th;
     if (G == 1) share(0);
-    else {
-        std::vector<std::thread> th;
+    else
         for (size_t g = 0; g < G; g++) th.emplace_back(share, g);
-        for (auto& t : th) t.join();
+
+    std::vector<int> hrc(G, BMPC_OK);
+    std::vector<uint32_t> hflags(G, 0);
+    std::vector<uint8_t> hpart(G * sizeof(G1XYZZ), 0);
+    if (share_h) {
+        // second contexts and coefficient buffers, created on first use and kept
+        int setup = BMPC_OK;
+        while (m->hctx.size() < G && setup == BMPC_OK) {
+            bmpc_ctx* c = nullptr;
+            setup = bmpc_ctx_create(m->ctx[m->hctx.size()]->device, &c);
+            if (setup == BMPC_OK) m->hctx.push_back(c);
+        }
+        const size_t need = mm * 32;
+        if (setup == BMPC_OK && need > m->ev_bytes) {
+            for (size_t g = 0; g < G && setup == BMPC_OK; g++) {
+                DeviceGuard dg(m->ctx[g]->device);
+                for (void* q : m->d_ev[g]) cudaFree(q);
+                m->d_ev[g].assign(g == 0 ? 3 : 1, nullptr);
+                for (auto& q : m->d_ev[g])
+                    if (cudaMalloc(&q, need) != cudaSuccess) setup = BMPC_ERR_CUDA;
+            }
+            m->ev_bytes = setup == BMPC_OK ? need : 0;
+        }
+        if (setup != BMPC_OK) {
+            for (auto& t : th) t.join();
+            m->err = "bmpc_multi_create_proof: setting up the shared H pipeline failed";
+            return setup;
+        }
+        const uint64_t* vec[3] = {S->a, S->b, S->c};
+        const size_t owners = G < 3 ? G : 3;
+        auto owner = [&](int k) { return (size_t)k % owners; };
+        // where vector k's coset evaluations are produced: device 0 keeps slot k, the others slot 0
+        auto ev_of = [&](int k) { const size_t o = owner(k); return o == 0 ? m->d_ev[0][k] : m->d_ev[o][0]; };
+        {   // stage 1: one vector per owner device
+            std::vector<std::thread> hb;
+            for (size_t o = 0; o < owners; o++)
+                hb.emplace_back([&, o]() {
+                    bmpc_ctx* hc = m->hctx[o];
+                    DeviceGuard dg(hc->device);
+                    for (int k = 0; k < 3; k++) {
+                        if (owner(k) != o || hrc[o]) continue;
+                        hrc[o] = bmpc_h_coset_evals_dev(hc, (uint64_t*)ev_of(k), exp, vec[k], nc, nullptr);
+                    }
+                    if (!hrc[o] && cudaStreamSynchronize(hc->own_stream) != cudaSuccess) hrc[o] = BMPC_ERR_CUDA;
+                });
+            for (auto& t : hb) t.join();
+        }
+        bool h_ok = true;
+        for (size_t o = 0; o < owners; o++) h_ok = h_ok && hrc[o] == BMPC_OK;
+        if (h_ok) {   // stage 2: device 0 pulls b's and c's evaluations and finishes the pipeline
+            bmpc_ctx* hc = m->hctx[0];
+            DeviceGuard dg(hc->device);
+            for (int k = 1; k < 3 && h_ok; k++) {
+                const size_t o = owner(k);
+                if (o == 0) continue;
+                cudaError_t e = m->ctx[o]->device == hc->device
+                                    ? cudaMemcpyAsync(m->d_ev[0][k], ev_of(k), need, cudaMemcpyDeviceToDevice, hc->own_stream)
+                                    : cudaMemcpyPeerAsync(m->d_ev[0][k], hc->device, ev_of(k), m->ctx[o]->device, need,
+                                                          hc->own_stream);
+                h_ok = e == cudaSuccess;
+            }
+            if (h_ok)
+                hrc[0] = bmpc_h_from_coset_evals_dev(hc, (uint64_t*)m->d_ev[0][0], (const uint64_t*)m->d_ev[0][1],
+                                                     (const uint64_t*)m->d_ev[0][2], exp, nullptr);
+            if (!h_ok || (!hrc[0] && cudaStreamSynchronize(hc->own_stream) != cudaSuccess)) hrc[0] = BMPC_ERR_CUDA;
+            h_ok = hrc[0] == BMPC_OK;
+        }
+        if (h_ok) {   // stage 3: every device pulls its slice of the scalars and runs its share of the H multiexp
+            std::vector<std::thread> hb;
+            for (size_t g = 0; g < G; g++)
+                hb.emplace_back([&, g]() {
+                    bmpc_ctx* ctx = m->hctx[g];
+                    std::lock_guard<std::mutex> lg(ctx->mu);
+                    DeviceGuard dg(ctx->device);
+                    cudaStream_t st = ctx->own_stream;
+                    StreamScope ss(ctx, st);
+                    auto run = [&]() -> int {
+                        const size_t lo = cuts[6].cut[g], hi = cuts[6].cut[g + 1], ns = hi - lo;
+                        // device 0 reads its slice in place; the others into their slot 0 (their own
+                        // coset evaluations are no longer needed)
+                        const uint64_t* d_sc = reinterpret_cast<const uint64_t*>(m->d_ev[0][0]) + 4 * lo;
+                        if (g != 0 && ns) {
+                            void* dst = m->d_ev[g][0];
+                            if (m->ctx[g]->device == m->ctx[0]->device)
+                                CK(cudaMemcpyAsync(dst, d_sc, ns * 32, cudaMemcpyDeviceToDevice, st));
+                            else
+                                CK(cudaMemcpyPeerAsync(dst, ctx->device, d_sc, m->ctx[0]->device, ns * 32, st));
+                            d_sc = reinterpret_cast<const uint64_t*>(dst);
+                        }
+                        int rc = multiexp_dev_locked(ctx, MP->h->part[g], cuts[6].base_off[g], d_sc, ns, nullptr, 0, nullptr,
+                                                     m->d_part[g], st, cnt[6], &hflags[g]);
+                        if (rc != BMPC_OK && rc != BMPC_ERR_UNEXPECTED_EOF && rc != BMPC_ERR_UNEXPECTED_IDENTITY) return rc;
+                        CK(cudaMemcpyAsync(ctx->h_stage + 1024, m->d_part[g], sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
+                        CK(cudaStreamSynchronize(st));
+                        memcpy(hpart.data() + g * sizeof(G1XYZZ), ctx->h_stage + 1024, sizeof(G1XYZZ));
+                        return BMPC_OK;
+                    };
+                    hrc[g] = run();
+                });
+            for (auto& t : hb) t.join();
+        }
+    }
+    for (auto& t : th) t.join();
+    if (share_h) {
+        for (size_t g = 0; g < G; g++)
+            if (hrc[g]) { m->err = bmpc_last_error(m->hctx[g]); return hrc[g]; }
+        for (size_t g = 0; g < G; g++) {        // the H partial is entry 4 of the six G1 sums (a_in, a_aux, b1_in, b1_aux, h, l)
+            memcpy(partials.data() + g * BMPC_PROOF_PARTIAL_BYTES + 4 * sizeof(G1XYZZ), hpart.data() + g * sizeof(G1XYZZ),
+                   sizeof(G1XYZZ));
+            flags[8 * g + 6] = hflags[g];
+        }
     }
     for (size_t g = 0; g < G; g++)
         if (rcs[g]) { m->err = bmpc_last_error(m->ctx[g]); return rcs[g]; }

@@ -22,9 +22,18 @@ from util import Q, decode, expected_from_dlogs, known_dlog_bases, rand_scalars
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def multi3():
-    w = bm.MultiWorker([0, 0, 0])
+@pytest.fixture(scope="module", params=["one-gpu-three-times", "all-gpus"])
+def multi3(request):
+    """the same GPU named three times (runs the whole plan on a one-GPU box), and, where the box has
+    several, all of them: the partial sums then really cross devices (cudaMemcpyPeerAsync)"""
+    if request.param == "all-gpus":
+        import torch
+        nd = torch.cuda.device_count()
+        if nd < 2:
+            pytest.skip("one GPU only")
+        w = bm.MultiWorker(list(range(min(nd, 8))))
+    else:
+        w = bm.MultiWorker([0, 0, 0])
     yield w
     w.close()
 
@@ -219,3 +228,37 @@ def test_folded_contribution_check(worker):
             assert ompc.verify_vector(E, pts_new, d2, pts_old) == ok
         matrixed.free()
         new.free()
+
+
+def test_multi_corner_splits(multi3):
+    """fewer bases than devices, an offset that skips whole devices, all-zero densities, and a base
+    vector that is longer than any exponent vector uses"""
+    nd = len(multi3)
+    # two bases over >= 3 devices: at least one device holds nothing
+    ks = rand_scalars(2, 430)
+    mb = _multi_bases(multi3, bm.G1, ks)
+    sc = rand_scalars(2, 431)
+    assert bm.multiexp(multi3, (mb, 0), bm.FullDensity(), bm.ints_to_limbs(sc)).wait() == expected_from_dlogs(bm.G1, ks, sc)
+    assert bm.multiexp(multi3, (mb, 1), bm.FullDensity(), bm.ints_to_limbs(sc[:1])).wait() == \
+        expected_from_dlogs(bm.G1, ks[1:], sc[:1])
+    with pytest.raises(bm.UnexpectedEof):
+        bm.multiexp(multi3, (mb, 1), bm.FullDensity(), bm.ints_to_limbs(sc)).wait()
+    mb.free()
+    # the offset starts on the last device; the devices before it get nothing to do
+    n = 64 * nd
+    ks = rand_scalars(n, 432)
+    mb = _multi_bases(multi3, bm.G1, ks)
+    start = n - 20
+    sc = rand_scalars(20, 433, "mixed")
+    got = bm.multiexp(multi3, (mb, start), bm.FullDensity(), bm.ints_to_limbs(sc)).wait()
+    assert got == expected_from_dlogs(bm.G1, ks[start:], sc)
+    # nothing dense: identity, whatever the offset
+    none = bm.DensityTracker.from_bits([False] * 300)
+    got = bm.multiexp(multi3, (mb, n + 5), none, bm.ints_to_limbs(rand_scalars(300, 434))).wait()
+    assert decode(bm.G1, got) is None
+    # a sparse map whose dense positions all map into the first device's slice
+    bits = [i % 50 == 0 for i in range(500)]
+    sc = rand_scalars(500, 435)
+    got = bm.multiexp(multi3, (mb, 0), bm.DensityTracker.from_bits(bits), bm.ints_to_limbs(sc)).wait()
+    assert got == expected_from_dlogs(bm.G1, ks, sc, bits, 0)
+    mb.free()
