@@ -48,7 +48,9 @@ int multiexp_enqueue(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
     uint32_t* d_flags = reinterpret_cast<uint32_t*>(ctx->d_stage);
     uint8_t* d_bytes = ctx->d_stage + 64;
     int mode = d_partial ? 1 : 0;
-    MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr, n_ref);
+    const size_t dense_hint = ctx->dense_hint;
+    ctx->dense_hint = 0;
+    MsmPlan p = msm_make_plan(ctx, bases, n, d_density != nullptr, n_ref, dense_hint);
     // histogram, offsets, cursors and task descriptors are 32-bit over the n * W (position, window)
     // pairs: refuse what would overflow them instead of corrupting the sort
     if (p.max_pairs >= ((size_t)1 << 32) - 1) {
@@ -464,6 +466,7 @@ int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, co
             CK(cudaMemcpyAsync(d_d, density_words, dw * 8, cudaMemcpyHostToDevice, st));
         }
     }
+    ctx->dense_hint = (density_words && n) ? popcount_bits(density_words, n) : 0;
     return multiexp_dev_locked(ctx, bases, base_offset, d_s, n, d_d, density_len, out, nullptr, st);
 }
 
@@ -1028,6 +1031,7 @@ int create_proof_common(bmpc_ctx* ctx, const bmpc_params* P, const bmpc_assignme
         if (!rc) {
             const size_t nj = SL.hi[j] - SL.lo[j];
             const uint64_t* dj = dens_src[j] >= 0 ? reinterpret_cast<const uint64_t*>(ctx->io + o_dens[j]) : nullptr;
+            ctx->dense_hint = dj ? popcount_bits(SL.dens[j], nj) : 0;
             rc = multiexp_enqueue(ctx, jobs[j].bases, SL.base_offset[j], jobs[j].sc, nj, dj, nj, nullptr, jobs[j].out,
                                   js, ctx->h_stage + 256 * j, &pend[j], SL.n_total[j]);
         }

@@ -94,6 +94,12 @@ struct bmpc_ctx {
     // staging for small results
     uint8_t* h_stage = nullptr;  // 4 KB pinned
     uint8_t* d_stage = nullptr;  // 4 KB
+    // Number of dense positions of the NEXT multiexp enqueued on this context, when its caller has the
+    // density words on the host (exact popcount; 0 = unknown).  The plan then sizes the slices, the
+    // scratch strides and the entry arrays for the points that really arrive instead of for one per
+    // position (create_proof: B density 0.5 -> slices and scratch strides twice too long).  Consumed
+    // (reset) by multiexp_enqueue; set under the context's lock.
+    size_t dense_hint = 0;
     // lanes of the asynchronous multiexp (multi.cu: bmpc_multiexp_async): child contexts on the same
     // device, each with its own stream, scratch arena and staging, handed out one per Waiter
     std::vector<bmpc_ctx*> lanes;
@@ -323,7 +329,15 @@ struct MsmSorted {      // outputs of the sort stage (device pointers into the a
     uint32_t* nsorted;  // device pointer to the number of entries in `sorted` (== off[nb]; padded in pair mode)
 };
 
-MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density, size_t n_ref = 0);
+MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density, size_t n_ref = 0,
+                      size_t n_dense = 0);
+// set bits among the first nbits of a bitvec's raw words (host)
+inline size_t popcount_bits(const uint64_t* words, size_t nbits) {
+    size_t full = nbits / 64, cnt = 0;
+    for (size_t i = 0; i < full; i++) cnt += (size_t)__builtin_popcountll(words[i]);
+    if (nbits % 64) cnt += (size_t)__builtin_popcountll(words[full] & ((1ull << (nbits % 64)) - 1));
+    return cnt;
+}
 uint32_t msm_table_window(size_t n_bases);  // window bits used for precomputed tables
 // count -> scan -> scatter; raises EOF / identity flags into d_flags[0]
 int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_t base_offset,

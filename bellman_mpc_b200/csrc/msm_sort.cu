@@ -61,7 +61,11 @@ uint32_t msm_table_window(size_t n_bases) {
     return pick_window(n_bases, lo, hi, true);
 }
 
-MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has_density, size_t n_ref) {
+MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n_pos, bool has_density, size_t n_ref,
+                      size_t n_dense) {
+    // n_pos exponent positions, of which n (<= n_pos; the exact count when the caller knows it) are
+    // dense and can contribute points: the geometry follows n, the density scan n_pos
+    const size_t n = (has_density && n_dense && n_dense < n_pos) ? n_dense : n_pos;
     MsmPlan p;
     MsmGeom& g = p.g;
     uint32_t c;
@@ -97,11 +101,11 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n, bool has
     g.tab_stride = tables ? (uint32_t)bases->n : 0u;
     size_t avg = n * (g.W / g.H) / g.B;
     g.L = (uint32_t)(2 * avg < 64 ? 64 : 2 * avg);
-    p.n = n;
+    p.n = n_pos;
     p.has_density = has_density;
     // the reference picks its window from the length of the whole exponent vector; a shard of a
     // larger multiexp passes that length so that "which error wins" is decided as the reference does
-    g.c_ref = reference_window(n_ref > n ? n_ref : n);
+    g.c_ref = reference_window(n_ref > n_pos ? n_ref : n_pos);
     g.top_skip = (254 / g.c_ref) * g.c_ref;
     p.nb = g.H * g.B;
     p.max_pairs = n * g.W;

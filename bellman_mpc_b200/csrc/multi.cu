@@ -56,12 +56,7 @@ void lane_release(bmpc_ctx* ctx, int lane) {
 }
 
 // ---- density bit helpers (host) ---------------------------------------------------------------
-inline size_t popcount_below(const uint64_t* words, size_t nbits) {      // set bits in [0, nbits)
-    size_t full = nbits / 64, cnt = 0;
-    for (size_t i = 0; i < full; i++) cnt += (size_t)__builtin_popcountll(words[i]);
-    if (nbits % 64) cnt += (size_t)__builtin_popcountll(words[full] & ((1ull << (nbits % 64)) - 1));
-    return cnt;
-}
+inline size_t popcount_below(const uint64_t* words, size_t nbits) { return popcount_bits(words, nbits); }
 // position of the k-th (0-based) set bit among the first nbits, or nbits if there are not that many;
 // words == NULL: every position is dense
 size_t dense_select(const uint64_t* words, size_t nbits, size_t k) {
@@ -193,6 +188,7 @@ int bmpc_multiexp_async(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offs
                 return fail(BMPC_ERR_CUDA, "bmpc_multiexp_async: density upload failed");
         }
         // the result lands in the lane's pinned staging; the caller's buffer is filled by wait()
+        lane->dense_hint = density_words ? popcount_bits(density_words, n) : 0;
         rc = multiexp_enqueue(lane, bases, base_offset, d_s, n, d_d, density_len, lane->h_stage + 2048, nullptr, st,
                               lane->h_stage, &w->pend);
         if (rc) return fail(rc, lane->err);
@@ -384,6 +380,7 @@ int bmpc_multi_multiexp(bmpc_multi* m, const bmpc_multi_bases* mb, size_t base_o
                     CK(cudaMemcpyAsync(d_d, dens.data(), dw * 8, cudaMemcpyHostToDevice, st));
                 }
             }
+            ctx->dense_hint = (d_d && ns) ? popcount_bits(dens.data(), ns) : 0;
             int rc = multiexp_dev_locked(ctx, mb->part[g], cuts.base_off[g], d_s, ns, d_d, ns, nullptr, m->d_part[g], st,
                                          n, &flags[g]);
             // a shard's own verdict is not the multiexp's: the flag words of all shards are ORed below
