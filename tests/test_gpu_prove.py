@@ -51,6 +51,21 @@ def test_xor_demo(worker):
         assert not og.verify_proof(E, params.vk, got, [int(not (a ^ b))])
 
 
+def test_full_size_r_s(worker):
+    """create_proof(circuit, params, r, s) with 255-bit r, s (prover.rs:176-181 takes them as arguments;
+    only create_random_proof fixes them): the seven scalar multiplications of the tail walk all 255 bits.
+    Bytes == the oracle prover's, and the verifier accepts."""
+    E = og.BLS12
+    rng = random.Random(99)
+    params = og.generate_random_parameters(E, og.xor_demo(None, None))
+    gp = upload_params(worker, params)
+    prover = og.synthesize_for_proving(E, og.xor_demo(True, True))
+    for r, s in ((rng.randrange(Q), rng.randrange(Q)), (Q - 1, 1), (0, 0)):
+        proof = bm.create_proof(to_gpu_assignment(prover), gp, bm.fr_to_mont([r])[0], bm.fr_to_mont([s])[0])
+        assert proof == og.create_proof_from_assignment(E, prover, params, r, s).to_bytes(E), (r, s)
+        assert og.verify_proof(E, params.vk, og.Proof.read(E, proof), [0])
+
+
 def test_mimc(worker):
     """config #1: the crate's MiMC circuit (src/mimc_mod.rs; 646 constraints -> domain 1024,
     MSM sizes 1023 / 645 / 2), proof bytes == known-trapdoor proof"""
