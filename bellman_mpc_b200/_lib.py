@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbellman_b200.so")
+# BMPC_LIB_PATH: another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("BMPC_LIB_PATH") or os.path.join(_HERE, "libbellman_b200.so")
 
 (OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_LENGTH_MISMATCH, ERR_CUDA, ERR_INVALID,
  ERR_INVALID_DATA) = range(8)
