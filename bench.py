@@ -66,6 +66,14 @@ def measured_peaks():
             peaks["aff_traffic_bytes"] = float(json.load(open(kp))["msm_accumulate_affine_g1"]["dram_bytes_total"])
         except Exception:
             pass
+    kp2 = os.path.join(ROOT, "profiles", "r02_ncu_kernel_summaries.json")     # the kernel as it is now
+    if os.path.exists(kp2):
+        try:
+            k2 = json.load(open(kp2))["msm_accumulate_affine_g1"]
+            peaks["aff_traffic_bytes"] = float(k2["dram_bytes_total"])
+            peaks["fmaheavy_pct"] = float(k2["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"])
+        except Exception:
+            pass
     ip = os.path.join(ROOT, "profiles", "r01_imad_peak.json")
     if os.path.exists(ip):
         try:
@@ -426,7 +434,7 @@ def run_ours(args):
                     "unit": "TMAC32/s", "frac": ach / peaks["mac32_per_s"],
                     "traffic": traffic, "algorithmic_bytes": bytes_per_point * n,
                     "traffic_ratio": (traffic / (bytes_per_point * n)) if traffic else None,
-                    "traffic_source": "profiles/ (ncu --set full of this command, 1 GPU, 2^24): dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                    "traffic_source": "profiles/r02_ncu_kernel_summaries.json (ncu --set full of this workload, 1 GPU, 2^24): dram__bytes_read.sum + dram__bytes_write.sum per launch",
                     "peak_source": "profiles/r01_imad_peak.json (bench/imad_peak.cu on this pool's B200: 32 MAC32/clk/SM)",
                     "work": f"executed: {ww.value} windows of c={cw.value} bits x {mul_per_add} Fp products x 300 MAC32 per point",
                     "kernel_ms": acc_ms, "launches_per_step": acc_cnt // max(args.steps, 1),
