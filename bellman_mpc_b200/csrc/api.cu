@@ -151,6 +151,8 @@ void bmpc_tuning::load() {
     ntt_no_direct = geti("BMPC_NTT_NO_DIRECT", 0);
     proof_slots = geti("BMPC_PROOF_SLOTS", 0);
     tail_quad = geti("BMPC_TAIL_QUAD", 1);
+    sort_radix = geti("BMPC_SORT_RADIX", -1);
+    rs_chunk_log = geti("BMPC_RS_CHUNK_LOG", 0);
 }
 
 // =============================================================================== C ABI

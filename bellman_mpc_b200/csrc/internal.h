@@ -52,6 +52,8 @@ struct bmpc_tuning {
     int subwindows = 1;            // BMPC_MSM_SUBWINDOWS
     int reduce_block = 0;          // BMPC_REDUCE_BLOCK
     int ntt_no_direct = 0;         // BMPC_NTT_NO_DIRECT
+    int sort_radix = -1;           // BMPC_SORT_RADIX: two-level partition sort, 0 never, 1 whenever possible, -1 automatic
+    int rs_chunk_log = 0;          // BMPC_RS_CHUNK_LOG: entries per block of rs_bucket_hist / rs_scatter (0: 2^12)
     int tail_quad = 1;             // BMPC_TAIL_QUAD: fold / final steps of the bucket reduction with four lanes per element (G1)
     int proof_slots = 0;           // BMPC_PROOF_SLOTS: 3 chains of multiexps in create_proof, 8 (one stream each), 0 auto
     void load();
@@ -312,6 +314,9 @@ struct MsmPlan {
     uint32_t pair_stride = 0, pair_cstride = 0;   // row pitch of the per-round task scans / their chunk sums
     size_t n = 0;
     bool has_density = false;
+    // two-level partition sort instead of the one-pass scatter (msm_sort_kernels.cuh: rs_*); radix_ok:
+    // geometry and size allow it, radix: chosen (never together with pair rounds, whose padding it lacks)
+    bool radix_ok = false, radix = false;
     size_t sort_bytes;  // scratch for everything except the curve-typed buffers
 };
 // (re)derives max_tasks and sort_bytes from g.L / pairs (called by msm_make_plan and again by

@@ -109,6 +109,14 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n_pos, bool
     g.top_skip = (254 / g.c_ref) * g.c_ref;
     p.nb = g.H * g.B;
     p.max_pairs = n * g.W;
+    // Two-level partition sort (msm_sort_kernels.cuh: rs_*): pays from a few million pairs up, where the
+    // one-pass scatter's random 4-byte stores stop being absorbed by L2.  BMPC_SORT_RADIX: 0 never,
+    // 1 whenever the geometry allows it, -1 (default) from 2^22 pairs and 2^13 buckets up.
+    {
+        const int knob = ctx->tune.sort_radix;
+        const bool fits = g.W <= RS_MAX_WINDOWS && (p.nb + RS_BIN_BUCKETS - 1) / RS_BIN_BUCKETS <= RS_MAX_BINS;
+        p.radix_ok = fits && (knob > 0 || (knob < 0 && p.max_pairs >= ((size_t)1 << 22) && p.nb >= (1u << 13)));
+    }
     // reduce: each thread owns S = 2^s_log consecutive buckets of one set (msm_reduce_kernel), blocks
     // of 256 threads.  S is the smallest power of two for which all H sets fit in ONE wave of
     // resident blocks (a second, nearly empty wave doubles the kernel time; 2 resident 256-thread
@@ -155,6 +163,8 @@ void msm_plan_sizes(MsmPlan& p) {
     b += ws_need(entries + 2, 4);   // sorted
     b += ws_need(64, 4) + ws_need(256, 4);
     b += ws_need(p.max_tasks, 16);     // task descriptors
+    p.radix = p.radix_ok && !p.pairs;
+    if (p.radix) b += ws_need(p.max_pairs + 2, 8) + 3 * ws_need(RS_MAX_BINS + 1, 4);   // entries, bin hist / off / cursor
     p.sort_bytes = b + 4096;
 }
 
@@ -219,7 +229,53 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     CK(cudaMemsetAsync(hist, 0, (size_t)(p.nb + 1) * 4, st));
     CK(cudaMemsetAsync(heavy_count, 0, 4, st));
     uint32_t nblocks = (uint32_t)((n + 255) / 256);
-    LAUNCH(ctx, msm_count_kernel, nblocks, 256, 0, st, in, g, hist, d_flags);
+    // ---- two-level partition sort: bins of RS_BIN_BUCKETS buckets, then the buckets of a bin
+    uint2* entries = nullptr;
+    uint32_t *bin_hist = nullptr, *bin_off = nullptr, *bin_cursor = nullptr;
+    const uint32_t nbins = (p.nb + RS_BIN_BUCKETS - 1) / RS_BIN_BUCKETS;
+    uint32_t rs_chunk = 0, rs_blocks = 0;
+    if (p.radix) {
+        entries = ws_take<uint2>(ctx, p.max_pairs + 2);
+        bin_hist = ws_take<uint32_t>(ctx, RS_MAX_BINS + 1);
+        bin_off = ws_take<uint32_t>(ctx, RS_MAX_BINS + 1);
+        bin_cursor = ws_take<uint32_t>(ctx, RS_MAX_BINS + 1);
+        if (!entries || !bin_hist || !bin_off || !bin_cursor) {
+            ctx->err = "msm workspace carve failed (partition sort)";
+            return BMPC_ERR_INVALID;
+        }
+        CK(cudaMemsetAsync(bin_hist, 0, (size_t)(RS_MAX_BINS + 1) * 4, st));
+        // tile of 1024 (or, for many windows, 512) positions: count kernel 256 threads x 4 (2), partition
+        // kernel 512 threads x 2 (1)
+        const int ppt = g.W <= RS_PPT4_MAX_WINDOWS ? 4 : 2;
+        const uint32_t tile = RS_THREADS * ppt;
+        const uint32_t tiles = (uint32_t)((n + tile - 1) / tile);
+        const size_t part_smem = (size_t)2 * RS_MAX_BINS * 4 + (size_t)tile * g.W * 8;
+        if (ppt == 4) {
+            CK(cudaFuncSetAttribute(rs_partition_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            LAUNCH(ctx, rs_bin_count_kernel<4>, tiles, RS_THREADS, nbins * 4, st, in, g, nbins, bin_hist, d_flags);
+            LAUNCH(ctx, rs_bin_scan_kernel, 1, BMPC_SCAN_THREADS, 0, st, bin_hist, nbins, bin_off, bin_cursor);
+            LAUNCH(ctx, rs_partition_kernel<2>, tiles, RS_PART_THREADS, part_smem, st, in, g, nbins, bin_cursor, entries);
+        } else {
+            CK(cudaFuncSetAttribute(rs_partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            LAUNCH(ctx, rs_bin_count_kernel<2>, tiles, RS_THREADS, nbins * 4, st, in, g, nbins, bin_hist, d_flags);
+            LAUNCH(ctx, rs_bin_scan_kernel, 1, BMPC_SCAN_THREADS, 0, st, bin_hist, nbins, bin_off, bin_cursor);
+            LAUNCH(ctx, rs_partition_kernel<1>, tiles, RS_PART_THREADS, part_smem, st, in, g, nbins, bin_cursor, entries);
+        }
+        // Entries per block of the bucket-side kernels.  A bucket's slice of `sorted` is completed by all
+        // the chunks of its bin, so its sectors must stay in L2 for as long as a chunk takes: what is in
+        // flight -- resident blocks x chunk x 4 bytes of output -- has to stay well below L2.  Measured at
+        // 2^24 points (sort stage in ms): 2^16 7.5, 2^14 3.7, 2^13 3.3, 2^12 3.0, 2^11 no better; with
+        // 2^10 buckets per bin a chunk of 2^12 still brings four entries per bucket, so one claim serves
+        // a run.  BMPC_RS_CHUNK_LOG: tuning knob.
+        rs_chunk = 1u << 12;
+        if (ctx->tune.rs_chunk_log >= 10 && ctx->tune.rs_chunk_log <= 20) rs_chunk = 1u << ctx->tune.rs_chunk_log;
+        rs_blocks = (uint32_t)((p.max_pairs + rs_chunk - 1) / rs_chunk);
+        if (!rs_blocks) rs_blocks = 1;
+        LAUNCH(ctx, rs_bucket_hist_kernel, rs_blocks, RS_THREADS, 0, st, (const uint2*)entries, (const uint32_t*)bin_off,
+               nbins, rs_chunk, hist);
+    } else {
+        LAUNCH(ctx, msm_count_kernel, nblocks, 256, 0, st, in, g, hist, d_flags);
+    }
     // pair mode: bucket offsets with every count rounded up to even, the pad slots keep BMPC_PAIR_PAD
     int rc = run_scan(ctx, hist, p.nb, p.pairs ? BMPC_SCAN_EVEN : 0, chunks, off, st);
     if (rc) return rc;
@@ -227,7 +283,11 @@ int msm_sort_run(bmpc_ctx* ctx, const MsmPlan& p, const bmpc_bases* bases, size_
     rc = run_scan(ctx, hist, p.nb, g.L, chunks, toff, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(cursor, off, (size_t)p.nb * 4, cudaMemcpyDeviceToDevice, st));
-    LAUNCH(ctx, msm_scatter_kernel, nblocks, 256, 0, st, in, g, cursor, sorted);
+    if (p.radix)
+        LAUNCH(ctx, rs_scatter_kernel, rs_blocks, RS_THREADS, 0, st, (const uint2*)entries, (const uint32_t*)bin_off,
+               nbins, rs_chunk, cursor, sorted);
+    else
+        LAUNCH(ctx, msm_scatter_kernel, nblocks, 256, 0, st, in, g, cursor, sorted);
     LAUNCH(ctx, msm_find_heavy_kernel, (p.nb + 255) / 256, 256, 0, st, toff, p.nb, heavy, heavy_count);
     CK(cudaMemsetAsync(bins, 0, 256 * 4, st));
     LAUNCH(ctx, task_bin_count_kernel, (p.nb + 255) / 256, 256, 0, st, off, toff, p.nb, g.L, bins);

@@ -74,21 +74,27 @@ __device__ __forceinline__ bool msm_prepare(const MsmInput& in, const MsmGeom& g
     return true;
 }
 
-// Warp-aggregated atomicAdd: lanes of the warp holding the same key are grouped with
-// match.any, one lane adds the group size and every lane gets base + its rank in the group.
-// With uniform scalars groups are singletons; with 0/1-heavy witnesses (most lanes hit the same
-// bucket) it removes the same-address serialisation in L2.  Must be called by all 32 lanes;
-// dead lanes pass live = false.
+// Warp-aggregated atomicAdd for skewed keys.  `match.any` groups ALL equal keys but costs a step per
+// distinct value in the warp (uniform scalars: 32 distinct buckets, ~250 cycles per call -- it was the
+// largest item of the count kernel and of every rs_* kernel when they used it).  What has to be
+// defused is one DOMINANT key (0/1-heavy witnesses: most lanes hit bucket 0; the short top window: all
+// lanes hit the same bin): the lanes holding the first live lane's key are found with one ballot and
+// added by their leader, every other lane adds for itself.  Must be called by all 32 lanes; dead
+// lanes pass live = false.
 __device__ __forceinline__ uint32_t warp_agg_add(uint32_t* counters, uint32_t key, bool live, bool want_pos) {
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t k = live ? key : (0xffffffe0u + lane);       // unique dummy keys for dead lanes
-    uint32_t grp = __match_any_sync(0xffffffffu, k);
-    uint32_t leader = __ffs(grp) - 1u;
+    const uint32_t lv = __ballot_sync(0xffffffffu, live);
+    if (!lv) return 0;
+    const uint32_t src = __ffs(lv) - 1u;
+    const uint32_t k0 = __shfl_sync(0xffffffffu, key, src);
+    const uint32_t grp = __ballot_sync(0xffffffffu, live && key == k0);
+    const bool in_grp = (grp >> lane) & 1u;
     uint32_t base = 0;
-    if (live && lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(grp));
+    if (lane == src) base = atomicAdd(counters + k0, (uint32_t)__popc(grp));
+    else if (live && !in_grp) base = atomicAdd(counters + key, 1u);
     if (!want_pos) return 0;
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(grp & ((1u << lane) - 1u));
+    uint32_t gbase = __shfl_sync(0xffffffffu, base, src);
+    return in_grp ? gbase + __popc(grp & ((1u << lane) - 1u)) : base;
 }
 
 // window w -> bucket set (w % H), table (w / H): with precomputed tables H == 1 and every window
@@ -155,9 +161,10 @@ __device__ __forceinline__ uint32_t scan_xform(uint32_t x, uint32_t L) {
     return L ? (x + L - 1u) / L : x;
 }
 
-// returns exclusive prefix of `v` across the block; total in *total (valid in all threads)
+// returns exclusive prefix of `v` across the block of NT threads; total in *total (valid in all threads)
+template <int NT = BMPC_SCAN_THREADS>
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t warp_sums[BMPC_SCAN_THREADS / 32];
+    __shared__ uint32_t warp_sums[NT / 32];
     __shared__ uint32_t block_total;
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = v;
@@ -168,13 +175,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t ws = lane < BMPC_SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
+        uint32_t ws = lane < NT / 32 ? warp_sums[lane] : 0u;
         uint32_t winc = ws;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= (uint32_t)o) winc += t;
         }
-        if (lane < BMPC_SCAN_THREADS / 32) warp_sums[lane] = winc - ws;
+        if (lane < NT / 32) warp_sums[lane] = winc - ws;
         if (lane == 31) block_total = winc;
     }
     __syncthreads();
@@ -226,6 +233,295 @@ scan_phase3_kernel(const uint32_t* in, uint32_t n, uint32_t L, const uint32_t* c
         ex += v[j];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = chunk_sums[nchunks];
+}
+
+// ================================================================ two-level partition sort
+// The one-pass scatter above writes every (position, window) pair to a random 4-byte slot of an
+// array far larger than L2 (2^24 points: 805 MB): each store dirties a 32-byte sector that is
+// evicted long before its other seven words arrive, so DRAM sees a read-modify-write per pair, and
+// every pair pays a returning atomic on a random cursor (6.3 ms at 2^24, long_scoreboard 142 cycles
+// per issue).  Here the pairs are first partitioned by BIN (RS_BIN_BUCKETS consecutive buckets) with
+// tile-local staging in shared memory -- runs of a bin leave the SM as contiguous 8-byte entries
+// {payload, bucket} -- and then scattered bin by bin: a block takes a chunk of one bin's entries,
+// ranks them on shared-memory cursors and claims its output ranges with ONE global atomic per
+// non-empty bucket of the chunk; its stores fall into the bin's slice of `sorted` (a few MB, L2
+// resident while the bin is being worked on).  The per-bucket histogram (bucket offsets, task
+// offsets) comes from the same chunks instead of 2^24 x W global atomics.
+//
+//   rs_bin_count    positions -> bin histogram (+ the EOF / identity flags)
+//   rs_bin_scan     bin offsets, bin cursors
+//   rs_partition    positions -> entries grouped by bin
+//   rs_bucket_hist  entries  -> per-bucket counts
+//   (scan: off, toff as before)
+//   rs_scatter      entries  -> sorted
+#define RS_BIN_LOG 10u
+#define RS_BIN_BUCKETS (1u << RS_BIN_LOG)
+#define RS_MAX_BINS 2048u
+#define RS_THREADS 256u
+#define RS_PART_THREADS 512u   // rs_partition: 16 warps per block, two blocks per SM
+#define RS_PPT4_MAX_WINDOWS 13u   // tile of 1024 positions: 1024 x 13 entries = 104 KB of staging, two blocks per SM
+#define RS_MAX_WINDOWS 27u        // tile of 512 positions: 512 x 27 entries = 108 KB
+
+// Shared-memory counters take plain atomics: lanes hitting the same counter are serialised by the
+// hardware at a few cycles each, which even for a warp full of one key costs no more than the ballots
+// and shuffles of an aggregated add -- and for the common case (distinct keys) a single instruction
+// without a warp-wide dependency, so the walks of a thread's positions overlap.
+__device__ __forceinline__ uint32_t warp_agg_add_sh(uint32_t* sh, uint32_t key, bool live, bool want_pos) {
+    uint32_t pos = 0;
+    if (live) pos = atomicAdd(sh + key, 1u);
+    return pos;
+}
+
+// The signed digits of one scalar, window by window (the three position-side rs_* kernels).  The
+// scalar is consumed by shifting a register copy right by c bits per window -- no indexed access to
+// the limbs (local memory) and no division for the window's bucket set / table.  A dead position
+// walks a zero scalar: every digit is 0.
+struct DigitWalk {
+    uint32_t r[8];
+    uint32_t carry, set_base, tab_off;
+    __device__ __forceinline__ void init(const uint32_t s[8], bool alive) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = alive ? s[k] : 0u;
+        carry = 0;
+        set_base = 0;
+        tab_off = 0;
+    }
+    // digit d of the next window (0: nothing to add), its sign, its bucket key and its table offset
+    __device__ __forceinline__ uint32_t next(const MsmGeom& g, bool& neg, uint32_t& key, uint32_t& tab) {
+        uint32_t d = (r[0] & ((1u << g.c) - 1u)) + carry;
+#pragma unroll
+        for (int k = 0; k < 7; k++) r[k] = __funnelshift_r(r[k], r[k + 1], g.c);
+        r[7] >>= g.c;
+        neg = d > (g.B);                 // B = 2^(c-1)
+        if (neg) { d = (1u << g.c) - d; carry = 1; } else carry = 0;
+        key = set_base + (d - 1u);
+        tab = tab_off;
+        set_base += g.B;
+        if (set_base == g.H * g.B) { set_base = 0; tab_off += g.tab_stride; }
+        return d;
+    }
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_bin_count_kernel(MsmInput in, MsmGeom g, uint32_t nbins, uint32_t* bin_hist, uint32_t* flags) {
+    extern __shared__ uint32_t rs_sh[];
+    uint32_t* hist = rs_sh;
+    for (uint32_t b = threadIdx.x; b < nbins; b += RS_THREADS) hist[b] = 0;
+    __syncthreads();
+    const size_t tile0 = (size_t)blockIdx.x * (RS_THREADS * PPT);
+    DigitWalk dw[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+        size_t i = tile0 + (size_t)p * RS_THREADS + threadIdx.x;
+        uint32_t base_idx = 0, s[8];
+        bool alive = msm_prepare(in, g, i, flags, true, base_idx, s);
+        dw[p].init(s, alive);
+    }
+    for (uint32_t w = 0; w < g.W; w++) {
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+            bool neg;
+            uint32_t key, tab;
+            uint32_t d = dw[p].next(g, neg, key, tab);
+            warp_agg_add_sh(hist, key >> RS_BIN_LOG, d != 0, false);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += RS_THREADS)
+        if (hist[b]) atomicAdd(bin_hist + b, hist[b]);
+}
+
+// single block: bin_off[nbins + 1] = exclusive scan of bin_hist; bin_cursor = copy of the starts
+__global__ void __launch_bounds__(BMPC_SCAN_THREADS)
+rs_bin_scan_kernel(const uint32_t* bin_hist, uint32_t nbins, uint32_t* bin_off, uint32_t* bin_cursor) {
+    uint32_t carry = 0;
+    for (uint32_t start = 0; start < nbins; start += BMPC_SCAN_THREADS) {
+        uint32_t idx = start + threadIdx.x;
+        uint32_t v = idx < nbins ? bin_hist[idx] : 0u;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (idx < nbins) { bin_off[idx] = ex + carry; bin_cursor[idx] = ex + carry; }
+        carry += total;
+    }
+    if (threadIdx.x == 0) bin_off[nbins] = carry;
+}
+
+// Tile of RS_PART_THREADS * PPT positions -> its entries, grouped by bin in shared memory, then written
+// as one run per bin at a range claimed from the bin's cursor.  Dynamic shared memory:
+// 2 * RS_MAX_BINS words + RS_PART_THREADS * PPT * W entries of 8 bytes.
+template <int PPT>
+__global__ void __launch_bounds__(RS_PART_THREADS)
+rs_partition_kernel(MsmInput in, MsmGeom g, uint32_t nbins, uint32_t* bin_cursor, uint2* entries) {
+    extern __shared__ uint32_t rs_sh[];
+    uint32_t* cur = rs_sh;                       // counts, then tile-local cursors
+    uint32_t* delta = rs_sh + RS_MAX_BINS;       // global position of local slot j of bin b = delta[b] + j
+    uint2* stage = reinterpret_cast<uint2*>(rs_sh + 2 * RS_MAX_BINS);
+    for (uint32_t b = threadIdx.x; b < RS_MAX_BINS; b += RS_PART_THREADS) cur[b] = 0;
+    __syncthreads();
+    const size_t tile0 = (size_t)blockIdx.x * (RS_PART_THREADS * PPT);
+    uint32_t base_idx[PPT];
+    bool alive[PPT];
+    {
+        DigitWalk dw[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+            size_t i = tile0 + (size_t)p * RS_PART_THREADS + threadIdx.x;
+            uint32_t s[8];
+            base_idx[p] = 0;
+            alive[p] = msm_prepare(in, g, i, nullptr, false, base_idx[p], s);
+            dw[p].init(s, alive[p]);
+        }
+        for (uint32_t w = 0; w < g.W; w++) {
+#pragma unroll
+            for (int p = 0; p < PPT; p++) {
+                bool neg;
+                uint32_t key, tab;
+                uint32_t d = dw[p].next(g, neg, key, tab);
+                warp_agg_add_sh(cur, key >> RS_BIN_LOG, d != 0, false);
+            }
+        }
+    }
+    __syncthreads();
+    // tile-local offsets of the bins (consecutive bins per thread) and one claim per non-empty bin
+    uint32_t v[RS_MAX_BINS / RS_PART_THREADS], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < RS_MAX_BINS / RS_PART_THREADS; k++) {
+        v[k] = cur[threadIdx.x * (RS_MAX_BINS / RS_PART_THREADS) + k];
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan<(int)RS_PART_THREADS>(sum, &total);
+#pragma unroll
+    for (uint32_t k = 0; k < RS_MAX_BINS / RS_PART_THREADS; k++) {
+        uint32_t b = threadIdx.x * (RS_MAX_BINS / RS_PART_THREADS) + k;
+        if (v[k]) delta[b] = atomicAdd(bin_cursor + b, v[k]) - ex;
+        cur[b] = ex;
+        ex += v[k];
+    }
+    __syncthreads();
+    {
+        DigitWalk dw[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {              // the scalars again (L1 / L2 hits)
+            size_t i = tile0 + (size_t)p * RS_PART_THREADS + threadIdx.x;
+            uint32_t s[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (alive[p]) load_scalar(in.scalars + i * 8, s);
+            dw[p].init(s, alive[p]);
+        }
+        for (uint32_t w = 0; w < g.W; w++) {
+#pragma unroll
+            for (int p = 0; p < PPT; p++) {
+                bool neg;
+                uint32_t key, tab;
+                uint32_t d = dw[p].next(g, neg, key, tab);
+                const bool live = d != 0;
+                uint32_t pos = warp_agg_add_sh(cur, key >> RS_BIN_LOG, live, true);
+                if (live) stage[pos] = make_uint2((base_idx[p] + tab) | (neg ? 0x80000000u : 0u), key);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < total; j += RS_PART_THREADS) {
+        uint2 e = stage[j];
+        entries[delta[e.y >> RS_BIN_LOG] + j] = e;
+    }
+}
+
+// first bin whose range reaches past entry position s: largest b with bin_off[b] <= s
+__device__ __forceinline__ uint32_t rs_find_bin(const uint32_t* bin_off, uint32_t nbins, uint32_t s) {
+    uint32_t lo = 0, hi = nbins;                 // invariant: bin_off[lo] <= s < bin_off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(bin_off + mid) <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// counts of one segment [s, e) of bin b's entries into sh[RS_BIN_BUCKETS] (zeroed here)
+#define RS_UNROLL 4u
+__device__ __forceinline__ void rs_segment_count(const uint2* entries, uint32_t s, uint32_t e, uint32_t* sh) {
+    for (uint32_t i = threadIdx.x; i < RS_BIN_BUCKETS; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t j0 = s; j0 < e; j0 += RS_UNROLL * RS_THREADS) {          // warp-uniform trip count
+        uint32_t key[RS_UNROLL];
+#pragma unroll
+        for (uint32_t u = 0; u < RS_UNROLL; u++) {
+            uint32_t j = j0 + u * RS_THREADS + threadIdx.x;
+            key[u] = j < e ? __ldg(&entries[j].y) : 0xffffffffu;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < RS_UNROLL; u++)
+            warp_agg_add_sh(sh, key[u] & (RS_BIN_BUCKETS - 1u), key[u] != 0xffffffffu, false);
+    }
+    __syncthreads();
+}
+
+// Block k owns entries [k * chunk, (k + 1) * chunk) and walks the bins that range crosses.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_bucket_hist_kernel(const uint2* entries, const uint32_t* bin_off, uint32_t nbins, uint32_t chunk,
+                      uint32_t* hist) {
+    __shared__ uint32_t sh[RS_BIN_BUCKETS];
+    const uint32_t total = __ldg(bin_off + nbins);
+    uint64_t s64 = (uint64_t)blockIdx.x * chunk;
+    if (s64 >= total) return;
+    uint32_t s = (uint32_t)s64;
+    const uint32_t e = (uint32_t)(s64 + chunk < total ? s64 + chunk : total);
+    uint32_t b = rs_find_bin(bin_off, nbins, s);
+    while (s < e) {
+        uint32_t be = __ldg(bin_off + b + 1);
+        uint32_t se = be < e ? be : e;
+        if (se > s) {
+            rs_segment_count(entries, s, se, sh);
+            for (uint32_t i = threadIdx.x; i < RS_BIN_BUCKETS; i += RS_THREADS)
+                if (sh[i]) atomicAdd(hist + (size_t)b * RS_BIN_BUCKETS + i, sh[i]);
+            __syncthreads();
+            s = se;
+        }
+        if (s < e) b++;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint2* entries, const uint32_t* bin_off, uint32_t nbins, uint32_t chunk,
+                  uint32_t* cursor, uint32_t* sorted) {
+    __shared__ uint32_t sh[RS_BIN_BUCKETS];
+    const uint32_t total = __ldg(bin_off + nbins);
+    uint64_t s64 = (uint64_t)blockIdx.x * chunk;
+    if (s64 >= total) return;
+    uint32_t s = (uint32_t)s64;
+    const uint32_t e = (uint32_t)(s64 + chunk < total ? s64 + chunk : total);
+    uint32_t b = rs_find_bin(bin_off, nbins, s);
+    while (s < e) {
+        uint32_t be = __ldg(bin_off + b + 1);
+        uint32_t se = be < e ? be : e;
+        if (se > s) {
+            rs_segment_count(entries, s, se, sh);
+            // one claim per non-empty bucket of the segment: sh[i] becomes this block's write cursor
+            for (uint32_t i = threadIdx.x; i < RS_BIN_BUCKETS; i += RS_THREADS) {
+                uint32_t c = sh[i];
+                if (c) sh[i] = atomicAdd(cursor + (size_t)b * RS_BIN_BUCKETS + i, c);
+            }
+            __syncthreads();
+            for (uint32_t j0 = s; j0 < se; j0 += RS_UNROLL * RS_THREADS) {
+                uint2 en[RS_UNROLL];
+#pragma unroll
+                for (uint32_t u = 0; u < RS_UNROLL; u++) {
+                    uint32_t j = j0 + u * RS_THREADS + threadIdx.x;
+                    en[u] = j < se ? __ldg(entries + j) : make_uint2(0u, 0xffffffffu);
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < RS_UNROLL; u++) {
+                    const bool live = en[u].y != 0xffffffffu;
+                    uint32_t pos = warp_agg_add_sh(sh, en[u].y & (RS_BIN_BUCKETS - 1u), live, true);
+                    if (live) sorted[pos] = en[u].x;
+                }
+            }
+            __syncthreads();
+            s = se;
+        }
+        if (s < e) b++;
+    }
 }
 
 // ------------------------------------------------------------- task ordering by size

@@ -15,14 +15,16 @@ from util import Q, decode, expected_from_dlogs, known_dlog_bases, rand_scalars
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["xyzz", "affine", "pairs"])
+@pytest.fixture(autouse=True, params=["xyzz", "affine", "pairs", "affine_radix"])
 def accumulate_kernel(request, monkeypatch, worker):
     """Every case runs through all three bucket-accumulation kernels: the XYZZ chain, the
     batched-affine tree (msm_affine.cuh; forced here, with 3 slices per job) and the rounds of pair
     additions (msm_pairs.cuh; forced: the automatic choice only takes them for multiexps that fill
-    the GPU)."""
+    the GPU).  `affine_radix` adds the two-level partition sort (rs_* kernels) at every size the
+    geometry allows, in place of the one-pass scatter the automatic choice keeps for small calls."""
     monkeypatch.setenv("BMPC_ACC_PAIRS", "1" if request.param == "pairs" else "0")
-    monkeypatch.setenv("BMPC_ACC_AFFINE", "1" if request.param == "affine" else "0")
+    monkeypatch.setenv("BMPC_ACC_AFFINE", "1" if request.param.startswith("affine") else "0")
+    monkeypatch.setenv("BMPC_SORT_RADIX", "1" if request.param == "affine_radix" else "0")
     monkeypatch.setenv("BMPC_AFF_FORCE_G", "3")
     worker.reload_env()
     yield request.param
