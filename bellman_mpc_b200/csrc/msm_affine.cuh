@@ -323,9 +323,14 @@ struct BlockCoop {
     // cycles per issue); without the tree's two Fp2 sites it is 197 KB and 4.5 % faster (2^21 points:
     // 31.5 -> 30.1 ms; the forward pass' product out of line as well: 32.4 ms, worse).  G1 (108 KB, no
     // instruction starvation) keeps them inlined: 0.3 % faster.
+    // (operands copied to registers first: multiplied straight out of shared memory the limbs are loaded
+    // in the middle of the carry chains and the lo/hi halves no longer pair into IMAD.WIDE -- see mul_cold)
     static __device__ __forceinline__ F mul_rare(const F& a, const F& b) {
         if constexpr (sizeof(F) > sizeof(Fp)) return F::mul_cold(a, b);
-        else return a * b;
+        else {
+            const F x = aff_ld(&a), y = aff_ld(&b);
+            return x * y;
+        }
     }
     F* P;
     F* I;
