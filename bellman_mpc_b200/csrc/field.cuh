@@ -247,10 +247,19 @@ struct Field {
     // Montgomery product a * b * R^-1 mod p, fully reduced.
     BMPC_HD friend Field operator*(const Field& a, const Field& b) {
         uint32_t even[N], odd[N];
+        // Both operands are read into registers BEFORE the first carry-chain statement.  When a or b lives
+        // in memory (shared-memory butterflies, twiddle tables, by-reference arguments) the compiler will not
+        // merge loads across the volatile asm statements: the lo and the hi half of a limb product then
+        // multiply two different registers and ptxas cannot pair them into one IMAD.WIDE.X -- the product
+        // becomes IMAD + IMAD.HI + two IADD3 per limb pair (Fr: 64 + 64 + 65 multiplier instructions instead
+        // of 129; the whole NTT and every out-of-line curve operation ran that way until round 3).
+        uint32_t al[N], bl[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { al[j] = a.l[j]; bl[j] = b.l[j]; }
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
-            mad_redc(even, odd, a.l, b.l[i], i == 0);
-            mad_redc(odd, even, a.l, b.l[i + 1], false);
+            mad_redc(even, odd, al, bl[i], i == 0);
+            mad_redc(odd, even, al, bl[i + 1], false);
         }
         // last step left the reduced limb in even[0] (== 0); merge the two chains
         even[0] = add_cc(even[0], odd[1]);
