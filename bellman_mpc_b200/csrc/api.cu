@@ -148,6 +148,7 @@ void bmpc_tuning::load() {
     acc_compact = geti("BMPC_ACC_COMPACT", 0);
     subwindows = geti("BMPC_MSM_SUBWINDOWS", 1);
     reduce_block = geti("BMPC_REDUCE_BLOCK", 0);
+    reduce_slog_add = geti("BMPC_REDUCE_SLOG_ADD", 0);
     ntt_no_direct = geti("BMPC_NTT_NO_DIRECT", 0);
     proof_slots = geti("BMPC_PROOF_SLOTS", 0);
     tail_quad = geti("BMPC_TAIL_QUAD", 1);

@@ -51,6 +51,7 @@ struct bmpc_tuning {
     int acc_compact = 0;           // BMPC_ACC_COMPACT
     int subwindows = 1;            // BMPC_MSM_SUBWINDOWS
     int reduce_block = 0;          // BMPC_REDUCE_BLOCK
+    int reduce_slog_add = 0;       // BMPC_REDUCE_SLOG_ADD: more buckets per reduce thread than one wave needs (x 2^k)
     int ntt_no_direct = 0;         // BMPC_NTT_NO_DIRECT
     int sort_radix = -1;           // BMPC_SORT_RADIX: two-level partition sort, 0 never, 1 whenever possible, -1 automatic
     int rs_chunk_log = 0;          // BMPC_RS_CHUNK_LOG: entries per block of rs_bucket_hist / rs_scatter (0: 2^12)

@@ -129,6 +129,7 @@ MsmPlan msm_make_plan(bmpc_ctx* ctx, const bmpc_bases* bases, size_t n_pos, bool
         size_t capacity = (size_t)sms * (bases->group == BMPC_G1 ? 2 : 1) * 256;
         uint32_t s_log = 0;
         while (s_log < g.c - 1 && (((size_t)g.H * g.B) >> s_log) > capacity) s_log++;
+        for (int k = 0; k < ctx->tune.reduce_slog_add && s_log < g.c - 1; k++) s_log++;   // BMPC_REDUCE_SLOG_ADD: tuning knob
         // Threads per reduce block.  The block's suffix scan and tree cost log2(rblock) additions each
         // with every resident warp busy; the same levels cost a product's latency only in
         // msm_fold_kernel (single warps spread over the SMs), so the blocks are kept small and the
