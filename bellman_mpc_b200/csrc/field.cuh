@@ -533,6 +533,22 @@ struct Fp2 {
     BMPC_HD friend Fp2 operator-(const Fp2& a, const Fp2& b) { return Fp2{a.c0 - b.c0, a.c1 - b.c1}; }
     BMPC_HD Fp2 neg() const { return Fp2{c0.neg(), c1.neg()}; }
     BMPC_HD Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
+    // BMPC_FP2_CALLS (device): the three Fp products of every Fp2 product are calls of the out-of-line
+    // routine (operands by value, in registers) instead of three inlined bodies.
+#if defined(__CUDA_ARCH__) && defined(BMPC_FP2_CALLS)
+    BMPC_HD friend Fp2 operator*(const Fp2& a, const Fp2& b) {
+        Fp t0 = Fp::mul_cold(a.c0, b.c0);
+        Fp t1 = Fp::mul_cold(a.c1, b.c1);
+        Fp t2 = Fp::mul_cold(a.c0 + a.c1, b.c0 + b.c1);
+        return Fp2{t0 - t1, t2 - t0 - t1};
+    }
+    BMPC_HD Fp2 sqr() const {
+        Fp s = c0 + c1;
+        Fp d = c0 - c1;
+        Fp m = Fp::mul_cold(c0, c1);
+        return Fp2{Fp::mul_cold(s, d), m.dbl()};
+    }
+#else
     BMPC_HD friend Fp2 operator*(const Fp2& a, const Fp2& b) {
         Fp t0 = a.c0 * b.c0;
         Fp t1 = a.c1 * b.c1;
@@ -545,6 +561,7 @@ struct Fp2 {
         Fp m = c0 * c1;
         return Fp2{s * d, m.dbl()};
     }
+#endif
     BMPC_COLD Fp2 inv() const {
         Fp n = (Fp::mul_cold(c0, c0) + Fp::mul_cold(c1, c1)).inv();
         return Fp2{Fp::mul_cold(c0, n), Fp::mul_cold(c1, n).neg()};

@@ -20,6 +20,8 @@ static AffKernel<F> aff_kernel(uint32_t K, uint32_t minb, uint32_t blk = 128) {
     if constexpr (sizeof(F) == sizeof(Fp)) {
         if (blk == 512) return msm_accumulate_affine_kernel<F, 384, 1, 512>;
         if (blk == 256) return msm_accumulate_affine_kernel<F, 384, 2, 256>;
+    } else {
+        if (blk == 256) return msm_accumulate_affine_kernel<F, 384, 1, 256>;   // G2: one block per SM at 255 registers
     }
     if (K == 384) {
         if (minb == 4) return msm_accumulate_affine_kernel<F, 384, 4>;
@@ -128,13 +130,17 @@ void GroupOps<F>::plan_affine(bmpc_ctx* ctx, MsmPlan& p) {
     uint32_t blk = sizeof(F) == sizeof(Fp) ? (p.nb >= (1u << 21) ? 512 : 256) : 128;
     if (tn.aff_blockdim) {
         uint32_t v = (uint32_t)tn.aff_blockdim;
-        if (v == 32 || v == 64 || v == 128 || ((v == 256 || v == 512) && sizeof(F) == sizeof(Fp))) blk = v;
+        if (v == 32 || v == 64 || v == 128 || v == 256 || (v == 512 && sizeof(F) == sizeof(Fp))) blk = v;
     }
     // measured at 2^24 (G1): K = 384 / 128 registers (4 blocks per SM) 59.5 ms, K = 128 61.5 ms,
     // 172 registers (2 blocks) 80 ms; XYZZ kernel 73.2 ms.  G2 at 2^22: 168 registers (3 blocks per
     // SM, 0.9 KB of spills) 60.3 ms, 252 registers (2 blocks) 65.0 ms, XYZZ kernel 72.0 ms.
     p.aff_K = tn.aff_ksel == 128 ? 128 : 384;
-    p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 3;
+    // G2, round 3: with the Fp products of every Fp2 product as calls (group_g2.cu: BMPC_FP2_CALLS) the
+    // kernel body is a fifth of the inlined 197 KB and the instruction cache stops being the limit; two
+    // blocks per SM at 255 registers (no spills) then beat three at 168 (2^21 points: inlined 29.4 ms,
+    // calls at 168 registers 27.6, calls at 255 registers 25.0, calls at 128 registers 31.1).
+    p.aff_minb = sizeof(F) == sizeof(Fp) ? 4 : 1;
     if (tn.aff_minb) {
         int v = tn.aff_minb;
         p.aff_minb = (v == 4 || v == 3) ? (uint32_t)v : 1u;
