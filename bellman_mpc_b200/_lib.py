@@ -26,6 +26,7 @@ EXPORTS = [
     "bmpc_bases_read", "bmpc_bases_dev_ptr", "bmpc_bases_free",
     "bmpc_multiexp", "bmpc_multiexp_dev", "bmpc_multiexp_partial_dev", "bmpc_multiexp_shard_dev",
     "bmpc_msm_flags_status", "bmpc_sum_partials",
+    "bmpc_multiexp_shard_enqueue_dev", "bmpc_shard_record_bytes", "bmpc_fold_shard_records",
     "bmpc_partial_bytes", "bmpc_msm_geometry", "bmpc_msm_accumulate_info",
     "bmpc_domain_from_coeffs", "bmpc_domain_from_coeffs_dev", "bmpc_domain_len", "bmpc_domain_exp",
     "bmpc_domain_into_coeffs", "bmpc_domain_dev_ptr", "bmpc_domain_free", "bmpc_domain_transform",
@@ -123,6 +124,9 @@ def load():
         "bmpc_multiexp_partial_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, vp, vp]),
         "bmpc_multiexp_shard_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, sz, vp, C.POINTER(u32), vp]),
         "bmpc_msm_flags_status": (i32, [u32]),
+        "bmpc_multiexp_shard_enqueue_dev": (i32, [vp, vp, sz, vp, sz, vp, sz, sz, vp, vp]),
+        "bmpc_shard_record_bytes": (sz, [i32]),
+        "bmpc_fold_shard_records": (i32, [vp, i32, vp, sz, sz, vp, C.POINTER(u32), vp]),
         "bmpc_sum_partials": (i32, [vp, i32, vp, sz, vp, vp]),
         "bmpc_partial_bytes": (sz, [i32]),
         "bmpc_msm_geometry": (i32, [vp, vp, sz, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),

@@ -445,6 +445,77 @@ int bmpc_multiexp_shard_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_
     return (rc == BMPC_ERR_UNEXPECTED_EOF || rc == BMPC_ERR_UNEXPECTED_IDENTITY) ? BMPC_OK : rc;
 }
 
+// Enqueue-only form of the shard call: nothing is synchronised; the shard's RECORD -- its XYZZ partial
+// followed by its raw flag word -- is left at d_record_out (bmpc_shard_record_bytes) in stream order, so
+// the caller can all-gather the records of all ranks and fold them with ONE synchronisation
+// (bmpc_fold_shard_records) instead of one per step.
+int bmpc_multiexp_shard_enqueue_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                                    const uint64_t* d_scalars, size_t n, const uint64_t* d_density_words,
+                                    size_t density_len, size_t n_total, void* d_record_out, void* stream) {
+    if (!ctx || !bases || !d_record_out || n_total < n) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    const size_t pb = bmpc_partial_bytes(bases->group);
+    MsmPending pend;
+    int rc = multiexp_enqueue(ctx, bases, base_offset, d_scalars, n, d_density_words, density_len, nullptr,
+                              d_record_out, st, ctx->h_stage, &pend, n_total);
+    if (rc) return rc;
+    uint8_t* tail = reinterpret_cast<uint8_t*>(d_record_out) + pb;
+    CK(cudaMemsetAsync(tail, 0, 16, st));
+    if (pend.st) CK(cudaMemcpyAsync(tail, ctx->d_stage, 4, cudaMemcpyDeviceToDevice, st));   // the flag word
+    return BMPC_OK;
+}
+
+size_t bmpc_shard_record_bytes(int group) { return bmpc_partial_bytes(group) + 16; }
+
+namespace {
+// records (partial + flag word, `stride` bytes apart) -> contiguous partials + OR of the flag words
+__global__ void shard_records_unpack_kernel(const uint32_t* rec, uint32_t stride_words, uint32_t count,
+                                            uint32_t pwords, uint32_t* contig, uint32_t* flags_or) {
+    const uint32_t i = blockIdx.x;
+    if (i >= count) return;
+    const uint32_t* r = rec + (size_t)i * stride_words;
+    for (uint32_t w = threadIdx.x; w < pwords; w += blockDim.x) contig[(size_t)i * pwords + w] = r[w];
+    if (threadIdx.x == 0 && r[pwords]) atomicOr(flags_or, r[pwords]);
+}
+}  // namespace
+
+// Folds `count` shard records (as left by bmpc_multiexp_shard_enqueue_dev, all-gathered by the caller;
+// `stride` bytes apart) on `stream`: sum of the partials -> out (uncompressed affine), OR of the flag words
+// -> *flags_or_out; the multiexp's status is bmpc_msm_flags_status(*flags_or_out), and `out` is only
+// meaningful when that is BMPC_OK.  One synchronisation.
+int bmpc_fold_shard_records(bmpc_ctx* ctx, int group, const void* d_records, size_t count, size_t stride,
+                            uint8_t* out, uint32_t* flags_or_out, void* stream) {
+    if (!ctx || !out || !flags_or_out || (!d_records && count)) return BMPC_ERR_INVALID;
+    const size_t pb = bmpc_partial_bytes(group);
+    if (pb == 0 || stride < pb + 4 || stride % 4 || count >= ((size_t)1 << 20)) return BMPC_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = pick_stream(ctx, stream);
+    StreamScope ss(ctx, st);
+    const size_t ob = group == BMPC_G1 ? 96 : 192;
+    int rr = ws_reserve(ctx, ws_need(count * pb + 256, 1));
+    if (rr) return rr;
+    uint32_t* contig = ws_take<uint32_t>(ctx, count * pb / 4 + 4);
+    if (!contig) return BMPC_ERR_INVALID;
+    uint32_t* d_for = reinterpret_cast<uint32_t*>(ctx->d_stage + 32);
+    uint8_t* d_bytes = ctx->d_stage + 64;
+    CK(cudaMemsetAsync(d_for, 0, 4, st));
+    if (count)
+        LAUNCH(ctx, shard_records_unpack_kernel, (uint32_t)count, 64, 0, st, (const uint32_t*)d_records,
+               (uint32_t)(stride / 4), (uint32_t)count, (uint32_t)(pb / 4), contig, d_for);
+    int rcs = group == BMPC_G1 ? GroupOps<Fp>::sum_partials(ctx, contig, (uint32_t)count, d_bytes, st)
+                               : GroupOps<Fp2>::sum_partials(ctx, contig, (uint32_t)count, d_bytes, st);
+    if (rcs) return rcs;
+    CK(cudaMemcpyAsync(ctx->h_stage, ctx->d_stage, 64 + ob, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *flags_or_out = *reinterpret_cast<const uint32_t*>(ctx->h_stage + 32);
+    memcpy(out, ctx->h_stage + 64, ob);
+    return BMPC_OK;
+}
+
 int bmpc_msm_flags_status(uint32_t flags_or) { return flags_to_status(flags_or); }
 
 int bmpc_multiexp(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset, const uint64_t* scalars,

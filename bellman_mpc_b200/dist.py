@@ -111,37 +111,45 @@ def sharded_multiexp(partial_fn, fold_fn, n, density_words, base_offset, group=N
 
 def gpu_sharded_multiexp(worker, bases_slice, scalars_dev_ptr, n_total, group=None, stream=None):
     """FullDensity sharded MSM on GPUs: `bases_slice` holds exactly this rank's slice of the bases,
-    `scalars_dev_ptr` its slice of the scalars (device).  Returns (status, uncompressed bytes)."""
+    `scalars_dev_ptr` its slice of the scalars (device).  Returns (status, uncompressed bytes).
+    The shard is only ENQUEUED (its record -- XYZZ partial + raw flag word -- stays on the device), the
+    records are all-gathered on the same stream and folded with one host synchronisation; the status
+    is the reference's for the whole vector (flag words ORed, multiexp.rs:244-249).  `stream` must be
+    torch's current stream (or None with torch on the context's stream): the all-gather is ordered
+    after the shard through it."""
     import ctypes as C
 
     import torch
     import torch.distributed as dist
     lib = worker._lib
     grp = bases_slice.group
-    pbytes = int(lib.bmpc_partial_bytes(grp))
+    rbytes = int(lib.bmpc_shard_record_bytes(grp))
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_range(n_total, world, rank)
     dev = torch.device("cuda", worker.device)
-    partial = torch.zeros(pbytes + 8, dtype=torch.uint8, device=dev)
+    record = torch.zeros(rbytes, dtype=torch.uint8, device=dev)
+    rc = lib.bmpc_multiexp_shard_enqueue_dev(worker.ctx, bases_slice.handle, 0, scalars_dev_ptr, hi - lo, None, 0,
+                                             n_total, record.data_ptr(), stream)
+    if rc != _lib.OK:
+        # the call itself failed (arguments, CUDA): every rank must still reach the collective; the
+        # failing rank's code travels in the high half of its flag word
+        record.zero_()
+        record[rbytes - 16 + 2] = rc          # flag word = 0x80000000 | rc << 16 (little-endian bytes)
+        record[rbytes - 16 + 3] = 0x80
+    gathered = torch.zeros(world * rbytes, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, record, group=group)
+    out = np.zeros(96 if grp == _lib.G1 else 192, dtype=np.uint8)
     flags = C.c_uint32(0)
-    rc = lib.bmpc_multiexp_shard_dev(worker.ctx, bases_slice.handle, 0, scalars_dev_ptr, hi - lo, None, 0, n_total,
-                                     partial.data_ptr(), C.byref(flags), stream)
-    partial[pbytes] = rc
-    partial[pbytes + 1] = flags.value
-    gathered = torch.zeros(world * (pbytes + 8), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(gathered, partial, group=group)
-    g = gathered.view(world, pbytes + 8)
-    tail = g[:, pbytes:pbytes + 2].cpu().tolist()
-    failed = next((int(t[0]) for t in tail if int(t[0]) != _lib.OK), None)
-    if failed is not None:
-        return failed, None
-    status = combine_flags(int(t[1]) for t in tail)
+    st = lib.bmpc_fold_shard_records(worker.ctx, grp, gathered.data_ptr(), world, rbytes,
+                                     out.ctypes.data_as(C.c_void_p), C.byref(flags), stream)
+    if st != _lib.OK:
+        return st, None
+    if flags.value & 0x80000000:             # some rank's call failed outright
+        return ((flags.value >> 16) & 0x7f) or _lib.ERR_INVALID, None
+    status = flags_status(flags.value)
     if status != _lib.OK:
         return status, None
-    parts = g[:, :pbytes].contiguous()
-    out = np.zeros(96 if grp == _lib.G1 else 192, dtype=np.uint8)
-    st = lib.bmpc_sum_partials(worker.ctx, grp, parts.data_ptr(), world, out.ctypes.data_as(C.c_void_p), stream)
-    return st, out.tobytes()
+    return _lib.OK, out.tobytes()
 
 
 # ------------------------------------------------------------------ create_proof over N GPUs

@@ -258,21 +258,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
 
-    pbytes = int(lib.bmpc_partial_bytes(grp))
-    partial = torch.zeros(pbytes, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros(world * pbytes, dtype=torch.uint8, device=dev)
-    out = np.zeros(pt_bytes, dtype=np.uint8)
+    # a rank's record: its XYZZ partial + its raw flag word (bmpc_multiexp_shard_enqueue_dev)
+    rbytes = int(lib.bmpc_shard_record_bytes(grp))
+    partial = torch.zeros(rbytes, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * rbytes, dtype=torch.uint8, device=dev)
     import ctypes as C
+    flags_or = C.c_uint32(0)
+    out = np.zeros(pt_bytes, dtype=np.uint8)
     optr = out.ctypes.data_as(C.c_void_p)
 
     def step_resident(sc_ptr):
         if world == 1:
             st = lib.bmpc_multiexp_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, optr, stream)
         else:
-            st = lib.bmpc_multiexp_partial_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, partial.data_ptr(), stream)
-            assert st == 0, st
+            # shard enqueued, records all-gathered, folded: ONE host synchronisation per step; the status is
+            # the reference's for the whole vector (flag words of all ranks ORed, multiexp.rs:244-249)
+            st = lib.bmpc_multiexp_shard_enqueue_dev(w.ctx, bases.handle, 0, sc_ptr, n, None, 0, n_total,
+                                                     partial.data_ptr(), stream)
+            assert st == 0, (st, lib.bmpc_last_error(w.ctx))
             dist.all_gather_into_tensor(gathered, partial)
-            st = lib.bmpc_sum_partials(w.ctx, grp, gathered.data_ptr(), world, optr, stream)
+            st = lib.bmpc_fold_shard_records(w.ctx, grp, gathered.data_ptr(), world, rbytes, optr,
+                                             C.byref(flags_or), stream)
+            if st == 0:
+                st = lib.bmpc_msm_flags_status(flags_or.value)
         assert st == 0, (st, lib.bmpc_last_error(w.ctx))
 
     def barrier():
@@ -463,7 +471,7 @@ def run_ours(args):
                        n * 32 >> 20, n * pt_bytes >> 20,
                        "" if args.no_precompute else "; with the %d window tables %d MiB per GPU" % (ww.value, ww.value * n * pt_bytes >> 20)),
                    "table_bytes_per_gpu": 0 if args.no_precompute else ww.value * n * pt_bytes,
-                   "parallelism": f"bases split x{world}, all-gather of {pbytes}-byte partials" if world > 1 else "single GPU",
+                   "parallelism": f"bases split x{world}, all-gather of {rbytes}-byte records (XYZZ partial + flag word), one host synchronisation per step" if world > 1 else "single GPU",
                    "setup_s": round(t_setup, 2)},
         "clocks": clocks.summary(),
         "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,

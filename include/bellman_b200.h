@@ -144,6 +144,20 @@ int  bmpc_multiexp_shard_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base
                              const uint64_t* d_scalars, size_t n,
                              const uint64_t* d_density_words, size_t density_len, size_t n_total,
                              void* d_partial_out, uint32_t* flags_out, void* stream);
+/* Enqueue-only shard call: no synchronisation.  The shard's record = its XYZZ partial followed by its raw
+ * flag word (bmpc_shard_record_bytes(group) bytes, 16-byte aligned) is left at d_record_out in stream
+ * order; all-gather the records of all ranks on the same stream and hand them to bmpc_fold_shard_records
+ * -- one host synchronisation per multiexp instead of two (a rank's step at 8 GPUs is ~11 ms, the
+ * synchronisations and launch gaps of the two-call form cost 0.2 ms of it). */
+int  bmpc_multiexp_shard_enqueue_dev(bmpc_ctx* ctx, const bmpc_bases* bases, size_t base_offset,
+                                     const uint64_t* d_scalars, size_t n,
+                                     const uint64_t* d_density_words, size_t density_len, size_t n_total,
+                                     void* d_record_out, void* stream);
+size_t bmpc_shard_record_bytes(int group);
+/* sum of the records' partials -> out (96 / 192 B uncompressed affine), OR of their flag words ->
+ * *flags_or_out (status = bmpc_msm_flags_status); records are `stride` bytes apart */
+int  bmpc_fold_shard_records(bmpc_ctx* ctx, int group, const void* d_records, size_t count, size_t stride,
+                             uint8_t* out, uint32_t* flags_or_out, void* stream);
 /* status of a whole multiexp from the OR of its shards' flag words (SURVEY 8a'/5) */
 int  bmpc_msm_flags_status(uint32_t flags_or);
 int  bmpc_sum_partials(bmpc_ctx* ctx, int group, const void* d_partials, size_t count,

@@ -137,6 +137,13 @@ extern "C" {
                                    density_len: usize, n_total: usize, d_partial_out: *mut c_void,
                                    flags_out: *mut u32, stream: *mut c_void) -> c_int;
     pub fn bmpc_msm_flags_status(flags_or: u32) -> c_int;
+    pub fn bmpc_multiexp_shard_enqueue_dev(ctx: *mut bmpc_ctx, bases: *const bmpc_bases, base_offset: usize,
+                                           d_scalars: *const u64, n: usize, d_density_words: *const u64,
+                                           density_len: usize, n_total: usize, d_record_out: *mut c_void,
+                                           stream: *mut c_void) -> c_int;
+    pub fn bmpc_shard_record_bytes(group: c_int) -> usize;
+    pub fn bmpc_fold_shard_records(ctx: *mut bmpc_ctx, group: c_int, d_records: *const c_void, count: usize,
+                                   stride: usize, out: *mut u8, flags_or_out: *mut u32, stream: *mut c_void) -> c_int;
     pub fn bmpc_sum_partials(ctx: *mut bmpc_ctx, group: c_int, d_partials: *const c_void, count: usize,
                              out: *mut u8, stream: *mut c_void) -> c_int;
     pub fn bmpc_partial_bytes(group: c_int) -> usize;

@@ -242,6 +242,60 @@ def test_error_precedence_across_shards(worker, world):
         assert got == exp == {0: "ok", 1: "identity", 2: "eof"}[bdist.flags_status(acc)]
 
 
+@pytest.mark.parametrize("group,world", [(bm.G1, 2), (bm.G1, 5), (bm.G2, 3)])
+def test_shard_records_one_sync(worker, group, world):
+    """The enqueue-only shard call and the one-synchronisation fold (bmpc_multiexp_shard_enqueue_dev /
+    bmpc_fold_shard_records): `world` shards run back to back on this GPU, each leaving its record
+    (XYZZ partial + raw flag word) in ONE buffer as an all-gather would; the fold must return the
+    bytes of the whole multiexp and the OR of the flag words.  Also: an identity base consumed by a
+    shard shows up in the folded flags, a rank with nothing to do contributes the identity."""
+    import ctypes as C
+    import torch
+    from bellman_mpc_b200 import dist as bdist
+    lib = worker._lib
+    n = 1000
+    ks, scalars = rand_scalars(n, 61), list(rand_scalars(n, 62, "mixed"))
+    scalars[bdist.shard_range(n, world, world - 1)[0]] = 12345       # the poisoned base is consumed
+    rb = int(lib.bmpc_shard_record_bytes(group))
+    assert rb == int(lib.bmpc_partial_bytes(group)) + 16
+    for poison in (False, True):
+        recs = torch.full((world * rb,), 0xAB, dtype=torch.uint8, device="cuda")   # stale bytes must not leak
+        keep = []
+        for r in range(world):
+            lo, hi = bdist.shard_range(n, world, r)
+            sl_ks = list(ks[lo:hi])
+            if poison and r == world - 1:
+                sl_ks[0] = 0                                          # identity base on the last shard
+            bases = known_dlog_bases(worker, group, sl_ks)
+            d_sc = torch.from_numpy(bm.ints_to_limbs(scalars[lo:hi]).view(np.int64)).cuda()
+            rc = lib.bmpc_multiexp_shard_enqueue_dev(worker.ctx, bases.handle, 0, d_sc.data_ptr(), hi - lo, None, 0, n,
+                                                     recs.data_ptr() + r * rb, None)
+            assert rc == 0, lib.bmpc_last_error(worker.ctx)
+            keep.append((bases, d_sc))
+        out = np.zeros(96 if group == bm.G1 else 192, dtype=np.uint8)
+        fl = C.c_uint32(0xffffffff)
+        rc = lib.bmpc_fold_shard_records(worker.ctx, group, recs.data_ptr(), world, rb, out.ctypes.data_as(C.c_void_p),
+                                         C.byref(fl), None)
+        assert rc == 0, lib.bmpc_last_error(worker.ctx)
+        if poison:
+            assert fl.value & 2 and lib.bmpc_msm_flags_status(fl.value) == bm._lib.ERR_UNEXPECTED_IDENTITY
+        else:
+            assert fl.value == 0
+            assert out.tobytes() == expected_from_dlogs(group, ks, scalars)
+        for bases, _ in keep:
+            bases.free()
+    # n == 0 on a rank: identity partial, zero flags
+    recs = torch.full((rb,), 0xCD, dtype=torch.uint8, device="cuda")
+    bases = known_dlog_bases(worker, group, ks[:4])
+    assert lib.bmpc_multiexp_shard_enqueue_dev(worker.ctx, bases.handle, 0, None, 0, None, 0, n, recs.data_ptr(), None) == 0
+    out = np.zeros(96 if group == bm.G1 else 192, dtype=np.uint8)
+    fl = C.c_uint32(7)
+    assert lib.bmpc_fold_shard_records(worker.ctx, group, recs.data_ptr(), 1, rb, out.ctypes.data_as(C.c_void_p),
+                                       C.byref(fl), None) == 0
+    assert fl.value == 0 and decode(group, out.tobytes()) is None
+    bases.free()
+
+
 @pytest.mark.parametrize("group,n,c", [(bm.G1, 5000, 0), (bm.G1, 3000, 9), (bm.G2, 1500, 0), (bm.G1, 1 << 16, 0)])
 def test_precomputed_tables(worker, group, n, c):
     """window tables 2^(cw) P_i (one bucket set, no doubling fold) give the same bytes, also with
