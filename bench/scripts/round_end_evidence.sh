@@ -13,3 +13,6 @@ print(d["roofline"]["frac"], d["roofline"]["kernel_ms"], d["roofline"]["share_of
 print({k:v for k,v in d.get("prove",{}).items() if k in ("value","all_s","error","matches_known_dlog_expectation")})
 print([ (x["log_m"], round(x["ms"],3)) for x in d.get("ntt",{}).get("sweep",[])])
 PY
+# launch list of two 2^22 proofs
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/evidence_launches_prove.csv python bench/prove_profile.py 22 > gpurun_out/evidence_ncu_prove.log 2>&1
+python bench/launch_summary.py gpurun_out/evidence_launches_prove.csv > gpurun_out/evidence_prove_launch_summary.csv 2>/dev/null; head -12 gpurun_out/evidence_prove_launch_summary.csv
