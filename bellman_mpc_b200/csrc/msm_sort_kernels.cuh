@@ -244,8 +244,9 @@ scan_phase3_kernel(const uint32_t* in, uint32_t n, uint32_t L, const uint32_t* c
 // tile-local staging in shared memory -- runs of a bin leave the SM as contiguous 8-byte entries
 // {payload, bucket} -- and then scattered bin by bin: a block takes a chunk of one bin's entries,
 // ranks them on shared-memory cursors and claims its output ranges with ONE global atomic per
-// non-empty bucket of the chunk; its stores fall into the bin's slice of `sorted` (a few MB, L2
-// resident while the bin is being worked on).  The per-bucket histogram (bucket offsets, task
+// non-empty bucket of the chunk; its stores fall into the bin's slice of `sorted` (~400 KB at 2^24
+// points), and what all resident blocks have in flight stays in L2 until the bin's other chunks have
+// completed the sectors (see the chunk size note in msm_sort.cu).  The per-bucket histogram (bucket offsets, task
 // offsets) comes from the same chunks instead of 2^24 x W global atomics.
 //
 //   rs_bin_count    positions -> bin histogram (+ the EOF / identity flags)
